@@ -1,0 +1,200 @@
+/*
+ * ksp_b200.h -- C ABI of the B200-native katsdpsigproc RFI-flagging hot path.
+ *
+ * This is the drop-in boundary.  The reference has no native library on this
+ * path: every kernel is a Mako template JIT-compiled through PyCUDA/PyOpenCL
+ * (reference src/katsdpsigproc/accel.py:165-208, cuda.py:182-187) and launched
+ * with CommandQueue.enqueue_kernel (cuda.py:442-459).  Each entry point below
+ * replaces one such (template, enqueue_kernel) pair, or one group of PyCUDA
+ * runtime calls, and is what the reference-side ctypes binding in
+ * INTEGRATION.md binds.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void*.
+ *   - every launch is asynchronous on `stream`, never synchronises, never
+ *     allocates: scratch memory is an explicit argument (the reference's rule
+ *     that temporaries are slots, rfi/device.py:1081-1091, fft.py:351-355).
+ *   - strides are in ELEMENTS of the array they describe.
+ *   - return value: 0 on success; > 0 is a cudaError_t; < 0 is one of KSP_E*.
+ *   - element (channel c, baseline b) of a channel-major array is p[c*stride+b];
+ *     of a baseline-major ("transposed", suffix _t) array it is p[b*stride+c].
+ */
+#ifndef KSP_B200_H
+#define KSP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KSP_ABI_VERSION 1
+
+/* argument errors (negative return values) */
+#define KSP_EINVAL (-1)      /* bad size / null pointer / unsupported combination */
+#define KSP_EALIGN (-2)      /* pointer or stride not aligned as documented */
+#define KSP_ETOOLARGE (-3)   /* exceeds a documented limit (channels, width, windows) */
+#define KSP_ESCRATCH (-4)    /* scratch buffer too small */
+
+/* complex64 amplitude rule: which host np.abs the result equals */
+#define KSP_ABS_NUMPY 0      /* numpy on AVX-512F hosts: L*sqrt(fma(r,r,1)), r = min/max */
+#define KSP_ABS_HYPOT 1      /* correctly rounded hypot (numpy without AVX-512F) */
+
+/* BackgroundFlags (reference rfi/device.py:40-46) */
+#define KSP_FLAGS_NONE 0
+#define KSP_FLAGS_CHANNEL 1
+#define KSP_FLAGS_FULL 2
+
+#define KSP_MAX_WINDOWS 7    /* sum-threshold window sizes 1 .. 2^(n-1) = 64 */
+#define KSP_MAX_WIDTH 63     /* median filter width (odd) */
+
+int ksp_abi_version(void);
+/* Text for a return code of any function below (static storage). */
+const char *ksp_error_string(int code);
+
+/* ------------------------------------------------------------------------
+ * Runtime shims: replace the PyCUDA calls made by reference cuda.py
+ * (Device :86-158, Context :163-255, CommandQueue :257-479, Event :71-84).
+ * ---------------------------------------------------------------------- */
+int ksp_device_count(int *count);                                   /* cuda.py:152-155 */
+int ksp_device_name(int device, char *buf, int buf_len);            /* cuda.py:98-100 */
+int ksp_device_attributes(int device, int *cc_major, int *cc_minor, int *sm_count,
+                          int *warp_size, size_t *total_mem, int *l2_bytes); /* :134-141 */
+int ksp_device_set(int device);                                     /* Context.__enter__ :243-245 */
+int ksp_device_get(int *device);
+int ksp_versions(int *runtime_version, int *driver_version);        /* cuda.py:106-110 */
+
+int ksp_malloc(void **ptr, size_t bytes);                           /* Context.allocate_raw :189-191 */
+int ksp_free(void *ptr);
+int ksp_host_alloc(void **ptr, size_t bytes);                       /* allocate_pinned :202-204 */
+int ksp_host_free(void *ptr);
+
+int ksp_stream_create(void **stream);                               /* CommandQueue.__init__ :257-270 */
+int ksp_stream_destroy(void *stream);
+int ksp_stream_synchronize(void *stream);                           /* finish :477-479 */
+int ksp_stream_query(void *stream);                                 /* 0 = idle, cudaErrorNotReady otherwise */
+int ksp_stream_wait_event(void *stream, void *event);               /* enqueue_wait_for_events :467-472 */
+
+int ksp_event_create(void **event, int timing);                     /* enqueue_marker :461-465 */
+int ksp_event_destroy(void *event);
+int ksp_event_record(void *event, void *stream);
+int ksp_event_synchronize(void *event);                             /* Event.wait :75-76 */
+int ksp_event_elapsed_ms(void *start, void *end, float *ms);        /* Event.time_since :78-81 */
+
+/* kind: 1 = host->device, 2 = device->host, 3 = device->device (cudaMemcpyKind) */
+int ksp_memcpy_async(void *dst, const void *src, size_t bytes, int kind, void *stream);
+                                                                    /* enqueue_read/write_buffer :272-289 */
+int ksp_memcpy_2d_async(void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                        size_t width_bytes, size_t height, int kind, void *stream);
+                                                                    /* enqueue_*_buffer_rect :299-431 */
+int ksp_memset_async(void *dst, int value, size_t bytes, void *stream); /* enqueue_zero_buffer :433-440 */
+
+/* L2 persistence window for the flagger's scratch (no reference equivalent;
+ * bytes == 0 clears it). */
+int ksp_stream_set_l2_window(void *stream, void *base, size_t bytes, float hit_ratio);
+
+/* ------------------------------------------------------------------------
+ * Kernels
+ * ---------------------------------------------------------------------- */
+
+/* Transpose.  dst[c*dst_stride + r] = src[r*src_stride + c], elem_size in
+ * {1, 2, 4, 8, 16} bytes.  Replaces transpose.mako:44-73 / transpose.py:146-167. */
+int ksp_transpose(void *stream, void *dst, const void *src, int64_t rows, int64_t cols,
+                  int64_t dst_stride, int64_t src_stride, int elem_size);
+
+/* Sliding-median background.  dev[c*dev_stride+b] = amp - median of the
+ * usable amplitudes in channels [c-width/2, c+width/2] of baseline b (host
+ * semantics: clipped windows, even counts averaged in float64, flagged/NaN
+ * samples skipped and output 0).  vis is complex64 (float32 pairs), or
+ * float32 amplitudes when is_amplitude.  flags: NULL, uint8[channels]
+ * (KSP_FLAGS_CHANNEL) or uint8[channels*flags_stride] (KSP_FLAGS_FULL).
+ * Replaces rfi/background_median_filter.mako:200-220 / rfi/device.py:311-325. */
+int ksp_background_median_filter(void *stream, const void *vis, float *dev, const uint8_t *flags,
+                                 int64_t channels, int64_t baselines, int64_t vis_stride,
+                                 int64_t dev_stride, int64_t flags_stride, int width,
+                                 int is_amplitude, int flag_mode, int abs_mode);
+
+/* Same, but writes baseline-major deviations dev_t[b*dev_t_stride + c]
+ * (background + transpose_deviations of rfi/device.py:1152-1157 in one pass). */
+int ksp_background_median_filter_t(void *stream, const void *vis, float *dev_t,
+                                   const uint8_t *flags, int64_t channels, int64_t baselines,
+                                   int64_t vis_stride, int64_t dev_t_stride, int64_t flags_stride,
+                                   int width, int is_amplitude, int flag_mode, int abs_mode);
+
+/* noise[b] = float32(1.4826 * median{|dev| : |dev| > 0}) per baseline; NaN if no
+ * such sample.  Baseline-major input.  Replaces rfi/madnz_t.mako:72-87 /
+ * rfi/device.py:594-607. */
+int ksp_madnz_t(void *stream, const float *dev_t, float *noise, int64_t channels,
+                int64_t baselines, int64_t stride);
+
+/* Same statistic on channel-major input (dev[c*stride + b]); no scratch needed
+ * (four radix passes over global memory, lane == baseline).  Replaces
+ * rfi/madnz.mako:105-123 / rfi/device.py:443-461. */
+int ksp_madnz(void *stream, const float *dev, float *noise, int64_t channels, int64_t baselines,
+              int64_t stride);
+
+/* flags = dev > float32(n_sigma * noise[b]) ? flag_value : 0.  rows/cols are
+ * those of the arrays as stored; noise is indexed by column, or by row when
+ * transposed.  Replaces rfi/threshold_simple.mako:27-40, threshold_simple_t.mako:28-42. */
+int ksp_threshold_simple(void *stream, const float *dev, const float *noise, uint8_t *flags,
+                         int64_t rows, int64_t cols, int64_t dev_stride, int64_t flags_stride,
+                         double n_sigma, int flag_value, int transposed);
+
+/* Offringa SumThreshold along channels of baseline-major data, windows
+ * 1..2^(n_windows-1).  Per-window threshold = float32((n_sigma*noise[b])*scales[w])
+ * with scales[w] = falloff^-w supplied by the caller (host formula,
+ * rfi/host.py:215,235).  Only windows fully inside the band are summed.
+ * Replaces rfi/threshold_sum.mako:49-132 / rfi/device.py:968-987. */
+int ksp_threshold_sum(void *stream, const float *dev_t, const float *noise, uint8_t *flags_t,
+                      int64_t channels, int64_t baselines, int64_t dev_stride,
+                      int64_t flags_stride, int n_windows, double n_sigma, const double *scales,
+                      int flag_value);
+
+/* Percentile5: dest[k*dest_stride + r], k = min, max, 25 %, 75 %, 50 % ("lower")
+ * of |src[r, first_col : first_col+n_cols]|; src float32, or complex64 when
+ * !is_amplitude (amplitude rule abs_mode, then pure selection).
+ * Replaces percentile.mako:115-140 / percentile.py:193-209. */
+int ksp_percentile5(void *stream, const void *src, float *dest, int64_t rows, int64_t src_stride,
+                    int64_t dest_stride, int64_t first_col, int64_t n_cols, int is_amplitude,
+                    int abs_mode);
+
+/* MaskedSum: dest[col] = sum_rows mask[row]*src[row*src_stride+col] (complex64),
+ * or of mask[row]*|src| (float32 dest) when use_amplitudes; float64 accumulation,
+ * one rounding.  Replaces maskedsum.mako:38-68 / maskedsum.py:141-156. */
+int ksp_maskedsum(void *stream, const void *src, const float *mask, void *dest, int64_t rows,
+                  int64_t cols, int64_t src_stride, int use_amplitudes, int abs_mode);
+
+/* ------------------------------------------------------------------------
+ * Fused flagger: the standard median + MAD + SumThreshold combination of
+ * rfi/device.py:1111-1166 in three launches per baseline chunk, with the
+ * intermediates (baseline-major deviations, bit-packed flags) kept in an
+ * L2-resident scratch instead of round-tripping through HBM.
+ * ---------------------------------------------------------------------- */
+typedef struct ksp_flagger_params {
+    int64_t channels, baselines;
+    int64_t vis_stride;          /* elements per channel row of vis */
+    int64_t flags_stride;        /* bytes per channel row of flags */
+    int64_t input_flags_stride;  /* KSP_FLAGS_FULL only */
+    int width;                   /* median width (odd) */
+    int is_amplitude;
+    int flag_mode;               /* KSP_FLAGS_* */
+    int abs_mode;                /* KSP_ABS_* */
+    int n_windows;               /* 0 = simple threshold */
+    int flag_value;
+    double n_sigma;
+    double scales[KSP_MAX_WINDOWS];
+    int64_t chunk_baselines;     /* 0 = choose from the device's L2 size */
+} ksp_flagger_params;
+
+size_t ksp_flagger_scratch_bytes(const ksp_flagger_params *p);
+/* baselines per chunk that ksp_flagger will use for these parameters */
+int64_t ksp_flagger_chunk_baselines(const ksp_flagger_params *p);
+int ksp_flagger(void *stream, const ksp_flagger_params *p, const void *vis,
+                const uint8_t *input_flags, float *noise, uint8_t *flags, void *scratch,
+                size_t scratch_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KSP_B200_H */

@@ -1,0 +1,123 @@
+// Min/max programs for the sliding median of 13 (4 outputs per step) and the
+// generic small-window median used at band edges and around flagged samples.
+// __host__ __device__ so that tools/test_median13.cu can check them on the CPU.
+#pragma once
+#include <math.h>
+
+#ifdef __CUDACC__
+#define KSP_HD __host__ __device__ __forceinline__
+#else
+#define KSP_HD inline
+#endif
+
+namespace ksp {
+
+#define KSP_CE(a, b)            \
+    {                           \
+        float lo_ = fminf(a, b); \
+        float hi_ = fmaxf(a, b); \
+        a = lo_;                \
+        b = hi_;                \
+    }
+
+// Ranks 3..6 (0-based, ascending) of ten values.  A 29-comparator sorting
+// network for 10 inputs pruned to the 52 min/max operations that reach wires
+// 3..6 (tools/median_network.py derives and verifies it with the 0-1 principle).
+KSP_HD void mid4_of_10(float v0, float v1, float v2, float v3, float v4, float v5, float v6,
+                       float v7, float v8, float v9, float &m0, float &m1, float &m2, float &m3)
+{
+    KSP_CE(v0, v5) KSP_CE(v1, v6) KSP_CE(v2, v7) KSP_CE(v3, v8) KSP_CE(v4, v9)
+    KSP_CE(v0, v3) KSP_CE(v1, v4) KSP_CE(v5, v8) KSP_CE(v6, v9)
+    KSP_CE(v0, v2) KSP_CE(v3, v6) KSP_CE(v7, v9)
+    v1 = fmaxf(v0, v1);
+    KSP_CE(v2, v4) KSP_CE(v5, v7)
+    v8 = fminf(v8, v9);
+    KSP_CE(v1, v2) KSP_CE(v3, v5) KSP_CE(v4, v6) KSP_CE(v7, v8)
+    v3 = fmaxf(v1, v3);
+    KSP_CE(v2, v5) KSP_CE(v4, v7)
+    v6 = fminf(v6, v8);
+    v3 = fmaxf(v2, v3);
+    v6 = fminf(v6, v7);
+    KSP_CE(v3, v4) KSP_CE(v5, v6) KSP_CE(v4, v5)
+    m0 = v3; m1 = v4; m2 = v5; m3 = v6;
+}
+
+// Median of the 7 values {m0<=m1<=m2<=m3} U {b0<=b1<=b2}: the 4th smallest.
+KSP_HD float median7_sorted43(float m0, float m1, float m2, float m3, float b0, float b1, float b2)
+{
+    float t0 = fmaxf(m0, b2);
+    float t1 = fmaxf(m1, b1);
+    float t2 = fmaxf(m2, b0);
+    return fminf(fminf(t0, t1), fminf(t2, m3));
+}
+
+// Four medians of 13 from 16 consecutive samples: out[j] = median(e[j .. j+12]).
+// All 16 samples must be ordinary numbers (no NaN).
+KSP_HD void median13x4(const float (&e)[16], int rot, float &o0, float &o1, float &o2, float &o3)
+{
+#define E(k) e[((k) + rot) & 15]
+    float m0, m1, m2, m3;
+    mid4_of_10(E(3), E(4), E(5), E(6), E(7), E(8), E(9), E(10), E(11), E(12), m0, m1, m2, m3);
+    // left extras {e0,e1,e2} / {e1,e2}; right extras {e13,e14} / {e13,e14,e15}
+    float p0 = fminf(E(1), E(2)), p1 = fmaxf(E(1), E(2));
+    float q0 = fminf(E(13), E(14)), q1 = fmaxf(E(13), E(14));
+    {   // output 0: extras e0, p0, p1
+        float x = E(0);
+        float b0 = fminf(x, p0), t = fmaxf(x, p0);
+        float b1 = fminf(t, p1), b2 = fmaxf(t, p1);
+        o0 = median7_sorted43(m0, m1, m2, m3, b0, b1, b2);
+    }
+    {   // output 1: extras p0, p1, e13
+        float x = E(13);
+        float b0 = fminf(x, p0), t = fmaxf(x, p0);
+        float b1 = fminf(t, p1), b2 = fmaxf(t, p1);
+        o1 = median7_sorted43(m0, m1, m2, m3, b0, b1, b2);
+    }
+    {   // output 2: extras e2, q0, q1
+        float x = E(2);
+        float b0 = fminf(x, q0), t = fmaxf(x, q0);
+        float b1 = fminf(t, q1), b2 = fmaxf(t, q1);
+        o2 = median7_sorted43(m0, m1, m2, m3, b0, b1, b2);
+    }
+    {   // output 3: extras q0, q1, e15
+        float x = E(15);
+        float b0 = fminf(x, q0), t = fmaxf(x, q0);
+        float b1 = fminf(t, q1), b2 = fmaxf(t, q1);
+        o3 = median7_sorted43(m0, m1, m2, m3, b0, b1, b2);
+    }
+#undef E
+}
+
+// Generic median of up to 13 samples with a validity mask (bit k <-> w[k]).
+// Returns false if no sample is valid.  lo/hi are the lower/upper medians (equal
+// when the count is odd).  Slow path: ~250 operations.
+KSP_HD bool median_masked13(const float (&w)[13], unsigned valid, float &lo, float &hi)
+{
+    const float inf = INFINITY;
+    float s[13];
+#pragma unroll
+    for (int k = 0; k < 13; k++) s[k] = ((valid >> k) & 1u) ? w[k] : inf;
+    // odd-even transposition sort, 13 rounds
+#pragma unroll
+    for (int r = 0; r < 13; r++) {
+#pragma unroll
+        for (int k = (r & 1); k + 1 < 13; k += 2) KSP_CE(s[k], s[k + 1])
+    }
+#ifdef __CUDA_ARCH__
+    int n = __popc(valid & 0x1fffu);
+#else
+    int n = __builtin_popcount(valid & 0x1fffu);
+#endif
+    if (n == 0) return false;
+    int il = (n - 1) >> 1, ih = n >> 1;
+    lo = s[0];
+    hi = s[0];
+#pragma unroll
+    for (int k = 1; k < 13; k++) {
+        lo = (k == il) ? s[k] : lo;
+        hi = (k == ih) ? s[k] : hi;
+    }
+    return true;
+}
+
+}  // namespace ksp

@@ -1,0 +1,128 @@
+// 2-D transpose through a padded shared-memory tile.
+//
+// Replaces reference transpose.mako:44-73 / transpose_base.mako:34-137 (tile in
+// local memory, diagonal block order to dodge partition camping on 2014 GPUs).
+// On B200 the address hash spreads tiles over the L2 slices by itself, so the
+// tile order is the plain one; what matters is that both the loads and the
+// stores of a warp cover whole 32-byte sectors.
+//
+//   * 4/8/16-byte elements: 32x32-element tile, 32x8 threads, 4 rows per thread;
+//     a warp reads 128/256/512 contiguous bytes and writes the same.
+//   * 1/2-byte elements (flags): 128x32... handled by the BYTES variant below: a
+//     64x64-element tile moved as 32-bit words (16 lanes per 64-byte row), and
+//     re-packed from shared memory so that the stores are 32-bit words too.
+#include "common.cuh"
+
+namespace {
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+transpose_tile_kernel(T *__restrict__ dst, const T *__restrict__ src, int64_t rows, int64_t cols,
+                      int64_t dst_stride, int64_t src_stride)
+{
+    __shared__ T tile[32][33];
+    const int64_t c0 = (int64_t) blockIdx.x * 32;
+    const int64_t r0 = (int64_t) blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int64_t r = r0 + ty + 8 * k, c = c0 + tx;
+        if (r < rows && c < cols) tile[ty + 8 * k][tx] = src[r * src_stride + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int64_t c = c0 + ty + 8 * k, r = r0 + tx;  // dst row = src column
+        if (c < cols && r < rows) dst[c * dst_stride + r] = tile[tx][ty + 8 * k];
+    }
+}
+
+// Byte transpose: 64 (src rows) x 64 (src cols) tile per block of 256 threads.
+// Loads and stores are 32-bit words when the geometry allows, else bytes.
+__global__ void __launch_bounds__(256)
+transpose_bytes_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int64_t rows,
+                       int64_t cols, int64_t dst_stride, int64_t src_stride, int vec_ok)
+{
+    __shared__ uint32_t tile[64][17];  // 64 rows x 64 bytes, pitch 68 bytes
+    const int64_t c0 = (int64_t) blockIdx.x * 64;
+    const int64_t r0 = (int64_t) blockIdx.y * 64;
+    const int t = threadIdx.x;
+    const int lane16 = t & 15, rowq = t >> 4;  // 16 words per row, 16 rows per pass
+    const bool full = vec_ok && (r0 + 64 <= rows) && (c0 + 64 <= cols);
+    if (full) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int r = rowq + 16 * k;
+            tile[r][lane16] =
+                *reinterpret_cast<const uint32_t *>(src + (r0 + r) * src_stride + c0 + 4 * lane16);
+        }
+    } else {
+        uint8_t *tb = reinterpret_cast<uint8_t *>(&tile[0][0]);
+        for (int i = t; i < 64 * 64; i += 256) {
+            int r = i >> 6, c = i & 63;
+            uint8_t v = 0;
+            if (r0 + r < rows && c0 + c < cols) v = src[(r0 + r) * src_stride + c0 + c];
+            tb[r * 68 + c] = v;
+        }
+    }
+    __syncthreads();
+    const uint8_t *tb = reinterpret_cast<const uint8_t *>(&tile[0][0]);
+    if (full) {
+        // output row = src column c (0..63); 16 words of 4 src rows each
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            int c = rowq + 16 * k;
+            int r = 4 * lane16;
+            uint32_t w = (uint32_t) tb[(r + 0) * 68 + c] | ((uint32_t) tb[(r + 1) * 68 + c] << 8) |
+                         ((uint32_t) tb[(r + 2) * 68 + c] << 16) |
+                         ((uint32_t) tb[(r + 3) * 68 + c] << 24);
+            *reinterpret_cast<uint32_t *>(dst + (c0 + c) * dst_stride + r0 + r) = w;
+        }
+    } else {
+        for (int i = t; i < 64 * 64; i += 256) {
+            int c = i >> 6, r = i & 63;
+            if (r0 + r < rows && c0 + c < cols) dst[(c0 + c) * dst_stride + r0 + r] = tb[r * 68 + c];
+        }
+    }
+}
+
+template <typename T>
+int launch_tile(cudaStream_t s, void *dst, const void *src, int64_t rows, int64_t cols,
+                int64_t dst_stride, int64_t src_stride)
+{
+    dim3 grid((unsigned) ksp_divup(cols, 32), (unsigned) ksp_divup(rows, 32));
+    if (grid.y > 65535) return KSP_ETOOLARGE;
+    transpose_tile_kernel<T><<<grid, dim3(32, 8), 0, s>>>((T *) dst, (const T *) src, rows, cols,
+                                                          dst_stride, src_stride);
+    KSP_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int ksp_transpose(void *stream, void *dst, const void *src, int64_t rows, int64_t cols,
+                             int64_t dst_stride, int64_t src_stride, int elem_size)
+{
+    if (rows < 0 || cols < 0 || dst_stride < rows || src_stride < cols) return KSP_EINVAL;
+    if (rows == 0 || cols == 0) return 0;
+    if (!dst || !src) return KSP_EINVAL;
+    cudaStream_t s = (cudaStream_t) stream;
+    if (((uintptr_t) dst | (uintptr_t) src) % (uintptr_t) elem_size) return KSP_EALIGN;
+    switch (elem_size) {
+    case 1: {
+        dim3 grid((unsigned) ksp_divup(cols, 64), (unsigned) ksp_divup(rows, 64));
+        if (grid.y > 65535) return KSP_ETOOLARGE;
+        int vec_ok = ((uintptr_t) dst % 4 == 0) && ((uintptr_t) src % 4 == 0) &&
+                     (dst_stride % 4 == 0) && (src_stride % 4 == 0);
+        transpose_bytes_kernel<<<grid, 256, 0, s>>>((uint8_t *) dst, (const uint8_t *) src, rows,
+                                                    cols, dst_stride, src_stride, vec_ok);
+        KSP_CHECK_LAUNCH();
+        return 0;
+    }
+    case 2: return launch_tile<uint16_t>(s, dst, src, rows, cols, dst_stride, src_stride);
+    case 4: return launch_tile<uint32_t>(s, dst, src, rows, cols, dst_stride, src_stride);
+    case 8: return launch_tile<uint2>(s, dst, src, rows, cols, dst_stride, src_stride);
+    case 16: return launch_tile<uint4>(s, dst, src, rows, cols, dst_stride, src_stride);
+    default: return KSP_EINVAL;
+    }
+}
