@@ -1,0 +1,311 @@
+"""Parity of every CUDA kernel, called through the C ABI, against the oracle.
+
+The checker is ``oracle.contract`` (plain C, float32 device contract) which is
+itself pinned to the reference host classes by ``test_oracle_contract.py`` and
+``test_oracle_golden.py``; where the golden fixtures hold reference outputs they
+are compared directly as well.  Shapes follow the reference's own device tests
+(test/rfi/test_background.py:78-104, test_noise_est.py:54-61,
+test_threshold.py:60-93, test_flagger.py:74-132, test_percentile.py:37-90,
+test_transpose.py:35-59, test_maskedsum.py:35-67).
+"""
+
+import numpy as np
+import pytest
+
+import cabi_util as cu
+from oracle import contract
+
+pytestmark = pytest.mark.gpu
+
+
+def complex_normal(rs, shape):
+    return (rs.standard_normal(shape) + 1j * rs.standard_normal(shape)).astype(np.complex64)
+
+
+def assert_same_f32(a, b):
+    """Bit-for-bit equal, NaNs included."""
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    assert a.shape == b.shape
+    bad = a.view(np.uint32) != b.view(np.uint32)
+    both_nan = np.isnan(a) & np.isnan(b)
+    bad &= ~both_nan
+    assert not bad.any(), (int(bad.sum()), np.argwhere(bad)[:5], a[bad][:5], b[bad][:5])
+
+
+# ------------------------------------------------------------------ transpose
+@pytest.mark.parametrize("shape", [(4, 5), (53, 7), (53, 81), (32, 64), (200, 333), (1, 1)])
+@pytest.mark.parametrize("dtype", [np.float32, np.uint8, np.complex64, np.uint16, np.complex128])
+@pytest.mark.parametrize("pad", [0, 3])
+def test_transpose(shape, dtype, pad):
+    rs = np.random.RandomState(1)
+    a = (rs.uniform(0, 250, shape)).astype(dtype)
+    out = cu.transpose(a, pad, pad)
+    np.testing.assert_array_equal(a.T, out)
+
+
+def test_transpose_bytes_vector_path():
+    rs = np.random.RandomState(2)
+    a = rs.randint(0, 256, (192, 320)).astype(np.uint8)
+    np.testing.assert_array_equal(a.T, cu.transpose(a))
+    np.testing.assert_array_equal(a.T, cu.transpose(a, 4, 8))
+
+
+# ------------------------------------------------------------------ background
+def bg_inputs(channels, baselines, seed=1):
+    rs = np.random.RandomState(seed)
+    vis = complex_normal(rs, (channels, baselines))
+    flags = (rs.random_sample((channels, baselines)) < 0.1).astype(np.uint8)
+    flags[:, min(3, baselines - 1)] = 1            # a fully flagged baseline
+    flags[40:60, :] = (flags[40:60, :] * 3) | 4    # fully flagged windows, values other than 0/1
+    return vis, flags
+
+
+@pytest.mark.parametrize("width", [5, 13, 1, 21])
+@pytest.mark.parametrize("flag_kind", ["none", "channel", "full"])
+@pytest.mark.parametrize("amplitudes", [False, True])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_background(abs_mode, width, flag_kind, amplitudes, transposed):
+    vis, flags = bg_inputs(417, 313)
+    if amplitudes:
+        vis = np.abs(vis)
+    fl = {"none": None, "channel": np.ascontiguousarray(flags[:, 7]), "full": flags}[flag_kind]
+    expect = contract.background(vis, width, fl, amplitudes, abs_mode)
+    out = cu.background(vis, width, fl, amplitudes, abs_mode, transposed, pad=5)
+    assert_same_f32(expect, out.T if transposed else out)
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (5, 3), (12, 40), (13, 33), (31, 64), (1500, 70)])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_background_small_and_long(abs_mode, shape, transposed):
+    vis, flags = bg_inputs(*shape, seed=3)
+    for fl in (None, flags):
+        expect = contract.background(vis, 13, fl, False, abs_mode)
+        out = cu.background(vis, 13, fl, False, abs_mode, transposed)
+        assert_same_f32(expect, out.T if transposed else out)
+
+
+def test_background_special_values(abs_mode):
+    rs = np.random.RandomState(4)
+    vis = complex_normal(rs, (300, 40))
+    vis[rs.random_sample(vis.shape) < 0.02] = np.nan
+    vis[rs.random_sample(vis.shape) < 0.02] = 0
+    vis[17, 3] = np.inf
+    vis[100:140, 5] = 0
+    vis[200, 7] = 1e-30 + 1e-41j
+    for transposed in (False, True):
+        expect = contract.background(vis, 13, None, False, abs_mode)
+        out = cu.background(vis, 13, None, False, abs_mode, transposed)
+        assert_same_f32(expect, out.T if transposed else out)
+
+
+def test_background_golden(golden, abs_mode):
+    """Reference-generated deviations (float64) rounded to float32."""
+    if abs_mode != contract.ABS_NUMPY:
+        pytest.skip("fixtures were generated on an AVX-512F host")
+    vis, flags = golden["bg_in_vis"], golden["bg_in_flags"]
+    for width in (5, 13):
+        for kind, fl in (("none", None), ("channel", np.ascontiguousarray(flags[:, 0])),
+                         ("full", flags)):
+            out = cu.background(vis, width, fl, False, abs_mode)
+            assert_same_f32(golden[f"bg_w{width}_{kind}"].astype(np.float32), out)
+        out = cu.background(golden["bg_in_amp"], width, flags, True, abs_mode)
+        assert_same_f32(golden[f"bg_w{width}_amp_full"].astype(np.float32), out)
+
+
+# ------------------------------------------------------------------ noise
+@pytest.mark.parametrize("transposed", [False, True])
+def test_madnz(golden, transposed):
+    dev = golden["noise_in_dev"]
+    expect, _ = contract.noise_mad(dev)
+    out = cu.madnz(np.ascontiguousarray(dev.T) if transposed else dev, transposed, pad=3)
+    assert_same_f32(expect, out)
+    ref = golden["noise_big"].astype(np.float32)
+    assert np.max(np.abs(out.view(np.int32) - ref.view(np.int32))) <= 1   # R4: <= 1 ulp of host
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+@pytest.mark.parametrize("channels", [1, 2, 6, 1000, 10000, 10001, 40000, 70001])
+def test_madnz_sizes(transposed, channels):
+    rs = np.random.RandomState(channels)
+    baselines = 5
+    dev = rs.standard_normal((channels, baselines)).astype(np.float32)
+    dev[rs.random_sample(dev.shape) < 0.08] = 0
+    dev[:, 2] = 0                                     # NaN result
+    if channels > 5:
+        dev[:, 3] = np.float32(0.5) * rs.randint(1, 4, channels)   # heavy ties
+        dev[1::2, 4] = 0
+    expect, _ = contract.noise_mad(dev)
+    out = cu.madnz(np.ascontiguousarray(dev.T) if transposed else dev, transposed)
+    assert_same_f32(expect, out)
+
+
+# ------------------------------------------------------------------ thresholds
+def test_threshold_simple(golden):
+    dev = golden["thr_in_dev"]
+    ramp = np.linspace(0.0, 50.0, 273).astype(np.float32)
+    out = cu.threshold_simple(dev, ramp, 11.0, pad=2)
+    np.testing.assert_array_equal(golden["thr_simple_ramp"], out)
+    out_t = cu.threshold_simple(np.ascontiguousarray(dev.T), ramp, 11.0, 7, True, pad=2)
+    np.testing.assert_array_equal(golden["thr_simple_ramp"] * 7, out_t.T)
+
+
+def check_sum(dev, noise, n_sigma, n_windows, rho, flag_value=1, pad=0):
+    expect = contract.threshold_sum(dev, noise, n_sigma, n_windows, rho, flag_value)
+    out = cu.threshold_sum(np.ascontiguousarray(dev.T), noise, n_sigma, n_windows, rho, flag_value,
+                           pad)
+    np.testing.assert_array_equal(expect, out.T)
+    return expect
+
+
+def test_threshold_sum_reference_cases(golden):
+    dev = golden["thr_in_dev"]
+    const = np.repeat(10.0, 273).astype(np.float32)
+    ramp = np.linspace(0.0, 50.0, 273).astype(np.float32)
+    np.testing.assert_array_equal(golden["thr_sum_const"], check_sum(dev, const, 11.0, 4, 1.2))
+    np.testing.assert_array_equal(golden["thr_sum_ramp"], check_sum(dev, ramp, 11.0, 4, 1.2, pad=7))
+    np.testing.assert_array_equal(golden["thr_sum_ramp_w7_fv5"],
+                                  check_sum(dev, ramp, 11.0, 7, 1.5, 5))
+
+
+@pytest.mark.parametrize("rho", [1.2, 1.5, 2.5])
+def test_threshold_sum_broad(golden, rho):
+    out = check_sum(golden["thr2_in_dev"], np.full(24, 1.0, np.float32), 3.0, 6, rho)
+    np.testing.assert_array_equal(golden[f"thr2_sum_w6_rho{rho}"], out)
+
+
+def test_threshold_sum_random_sweep():
+    rs = np.random.RandomState(11)
+    for case in range(40):
+        channels = int(rs.choice([1, 2, 3, 17, 31, 32, 33, 64, 65, 300, 1025, 4096]))
+        dev = rs.standard_normal((channels, 6)).astype(np.float32)
+        if channels > 40:
+            for bl in range(6):
+                for _ in range(1 + channels // 400):
+                    s = rs.randint(0, channels - 10)
+                    dev[s:s + rs.randint(1, 90), bl] += rs.uniform(1.0, 8.0)
+        noise = rs.uniform(0.5, 2.0, 6).astype(np.float32)
+        n_windows = int(rs.choice([1, 2, 4, 5, 7]))
+        check_sum(dev, noise, float(rs.choice([2.5, 3.0, 4.5])), n_windows,
+                  float(rs.choice([1.2, 1.5, 2.5])), pad=int(rs.choice([0, 1, 4])))
+
+
+@pytest.mark.parametrize("channels", [32768, 32769, 40000, 70000])
+def test_threshold_sum_long_rows(channels):
+    """Rows longer than one block's span are processed in overlapping chunks."""
+    rs = np.random.RandomState(5)
+    dev = rs.standard_normal((channels, 3)).astype(np.float32)
+    for bl in range(3):
+        for _ in range(60):
+            s = rs.randint(0, channels - 100)
+            dev[s:s + rs.randint(1, 100), bl] += rs.uniform(1.0, 6.0)
+    # interference straddling the chunk seams
+    for seam in (32768 - 128, 32768 - 64, 2 * (32768 - 256)):
+        if seam + 80 < channels:
+            dev[seam - 40:seam + 40, 1] += 2.5
+    noise = np.array([1.0, 0.9, 1.1], np.float32)
+    check_sum(dev, noise, 3.0, 7, 1.2)
+
+
+def test_threshold_sum_nan_noise_and_ties():
+    dev = np.ones((64, 3), np.float32)
+    noise = np.array([np.nan, 1.0 / 11.0, -1.0], np.float32)
+    check_sum(dev, noise, 11.0, 7, 1.2)
+
+
+# ------------------------------------------------------------------ fused flagger
+@pytest.mark.parametrize("case", ["flg", "cfg1"])
+@pytest.mark.parametrize("n_windows", [1, 4, 7])
+def test_flagger_fused(golden, abs_mode, case, n_windows):
+    vis = golden[f"{case}_in_vis"]
+    in_flags = golden["flg_in_flags"] if case == "flg" else None
+    variants = [None] if in_flags is None else [None, np.ascontiguousarray(in_flags[:, 0]), in_flags]
+    for fl in variants:
+        flags, dev, noise = contract.flagger(vis, fl, n_windows=n_windows, abs_mode=abs_mode)
+        out_flags, out_noise = cu.flagger(vis, fl, n_windows=n_windows, abs_mode=abs_mode, pad=3)
+        assert_same_f32(noise, out_noise)
+        np.testing.assert_array_equal(flags, out_flags)
+        # several chunks, ragged last chunk
+        out_flags, out_noise = cu.flagger(vis, fl, n_windows=n_windows, abs_mode=abs_mode,
+                                          chunk_baselines=32)
+        assert_same_f32(noise, out_noise)
+        np.testing.assert_array_equal(flags, out_flags)
+
+
+def test_flagger_fused_golden(golden, abs_mode):
+    """Flags produced by the unmodified reference FlaggerHost."""
+    if abs_mode != contract.ABS_NUMPY:
+        pytest.skip("fixtures were generated on an AVX-512F host")
+    out_flags, out_noise = cu.flagger(golden["cfg1_in_vis"], n_windows=7, abs_mode=abs_mode)
+    np.testing.assert_array_equal(golden["cfg1_flags"], out_flags)
+    ref = golden["cfg1_noise"].astype(np.float32)
+    assert np.max(np.abs(out_noise.view(np.int32) - ref.view(np.int32))) <= 1
+    for kind, fl in (("none", None), ("channel", np.ascontiguousarray(golden["flg_in_flags"][:, 0])),
+                     ("full", golden["flg_in_flags"])):
+        for nw in (4, 7):
+            out_flags, _ = cu.flagger(golden["flg_in_vis"], fl, n_windows=nw, abs_mode=abs_mode)
+            np.testing.assert_array_equal(golden[f"flg_sum{nw}_{kind}"], out_flags)
+
+
+def test_flagger_fused_medium(abs_mode):
+    """4096 x 200 with injected spikes and narrowband lines: fused == contract, stage by stage."""
+    rs = np.random.RandomState(7)
+    channels, baselines = 4096, 200
+    vis = complex_normal(rs, (channels, baselines))
+    spikes = rs.random_sample(vis.shape) < 1 / 64
+    vis += (spikes * (rs.random_sample(vis.shape) * 20 + 50)
+            * np.exp(2j * np.pi * rs.random_sample(vis.shape))).astype(np.complex64)
+    vis[1000:1037, :] += 3.0
+    flags, dev, noise = contract.flagger(vis, None, n_windows=7, abs_mode=abs_mode)
+    out_flags, out_noise = cu.flagger(vis, None, n_windows=7, abs_mode=abs_mode, chunk_baselines=96)
+    assert_same_f32(noise, out_noise)
+    np.testing.assert_array_equal(flags, out_flags)
+
+
+# ------------------------------------------------------------------ helpers
+@pytest.mark.parametrize("shape,column_range", [((4096, 1), None), ((4096, 4029), None),
+                                                ((64, 300), (8, 280)), ((27, 301), (0, 301)),
+                                                ((3, 50000), None), ((2, 70001), (5, 70000))])
+@pytest.mark.parametrize("is_amplitude", [True, False])
+def test_percentile5(abs_mode, shape, column_range, is_amplitude):
+    rs = np.random.RandomState(1)
+    rows, cols = shape
+    rows = min(rows, 64)
+    if is_amplitude:
+        src = np.abs(rs.standard_normal((rows, cols))).astype(np.float32)
+    else:
+        src = complex_normal(rs, (rows, cols))
+    expect = contract.percentile5(src, column_range, abs_mode)
+    out = cu.percentile5(src, column_range, abs_mode, pad=3)
+    assert_same_f32(expect, out)
+    data = np.abs(src)
+    if column_range:
+        data = data[:, column_range[0]:column_range[1]]
+    ref = np.percentile(data, [0, 100, 25, 75, 50], axis=1, method="lower").astype(np.float32)
+    if is_amplitude or abs_mode == contract.detect_abs_mode():
+        assert_same_f32(ref, out)
+
+
+def test_percentile5_golden(golden, abs_mode):
+    assert_same_f32(golden["pct_amp_all"], cu.percentile5(golden["pct_in_amp"]))
+    assert_same_f32(golden["pct_amp_range"], cu.percentile5(golden["pct_in_amp"], (10, 290)))
+    if abs_mode == contract.ABS_NUMPY:
+        assert_same_f32(golden["pct_cplx_all"], cu.percentile5(golden["pct_in_cplx"], None, abs_mode))
+
+
+@pytest.mark.parametrize("cols", [2, 4029, 4030, 4031, 4032])
+@pytest.mark.parametrize("use_amplitudes", [False, True])
+def test_masked_sum(abs_mode, cols, use_amplitudes):
+    rs = np.random.RandomState(1)
+    rows = 4096
+    src = complex_normal(rs, (rows, cols))
+    mask = (rs.random_sample(rows) < 0.9).astype(np.float32)
+    expect = contract.masked_sum(src, mask, use_amplitudes, abs_mode)
+    out = cu.masked_sum(src, mask, use_amplitudes, abs_mode, pad=3)
+    scale = np.sum(np.abs(src) * mask[:, None], axis=0)
+    assert np.all(np.abs(expect - out) <= 1e-7 * scale)
+    # the reference test's expression (test/test_maskedsum.py:62-67), evaluated in float64 so that
+    # numpy's own float32 summation error (~2e-6 here) does not mask ours; tolerance as there
+    data = (np.abs(src).astype(np.float64) if use_amplitudes else src.astype(np.complex128))
+    ref = np.sum(data * mask[:, None], axis=0)
+    assert np.all(np.abs(ref - out) <= 1e-6 * scale)
