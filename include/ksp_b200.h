@@ -194,6 +194,21 @@ int ksp_flagger(void *stream, const ksp_flagger_params *p, const void *vis,
                 const uint8_t *input_flags, float *noise, uint8_t *flags, void *scratch,
                 size_t scratch_bytes);
 
+/* ------------------------------------------------------------------------
+ * Introspection (no reference equivalent; used by bench.py and the tests).
+ * ---------------------------------------------------------------------- */
+/* Number of kernels this library has launched in this process so far. */
+int ksp_kernel_launch_count(unsigned long long *count);
+
+/* Per-stage timing of ksp_flagger.  While enabled, ksp_flagger records CUDA events
+ * on its own stream around every stage launch; ksp_profile_read waits for them,
+ * sums the elapsed milliseconds and launch counts per stage (0 background,
+ * 1 noise, 2 threshold, 3 flag expansion; n_stages >= 4) and resets the record.
+ * Off by default: the timed path records no events. */
+#define KSP_N_STAGES 4
+int ksp_profile_enable(int on);
+int ksp_profile_read(double *stage_ms, int *stage_launches, int n_stages);
+
 #ifdef __cplusplus
 }
 #endif

@@ -116,6 +116,9 @@ PROTOTYPES = {
     ),
     "ksp_maskedsum": (
         c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int]),
+    "ksp_kernel_launch_count": (c_int, [POINTER(ctypes.c_ulonglong)]),
+    "ksp_profile_enable": (c_int, [c_int]),
+    "ksp_profile_read": (c_int, [POINTER(c_double), POINTER(c_int), c_int]),
     "ksp_flagger_scratch_bytes": (c_size_t, [POINTER(FlaggerParams)]),
     "ksp_flagger_chunk_baselines": (c_int64, [POINTER(FlaggerParams)]),
     "ksp_flagger": (
@@ -158,6 +161,28 @@ def check(code: int, what: str) -> None:
 def call(name: str, *args) -> None:
     """Call an int-returning entry point and raise on failure."""
     check(getattr(load(), name)(*args), name)
+
+
+def kernel_launch_count() -> int:
+    """Kernels launched by the library in this process so far."""
+    count = ctypes.c_ulonglong()
+    call("ksp_kernel_launch_count", byref(count))
+    return count.value
+
+
+STAGE_NAMES = ("background", "noise", "threshold", "expand_flags")
+
+
+def profile_enable(on: bool) -> None:
+    call("ksp_profile_enable", int(on))
+
+
+def profile_read() -> dict:
+    """{stage: (milliseconds, launches)} accumulated by ``ksp_flagger`` since the last read."""
+    ms = (c_double * len(STAGE_NAMES))()
+    n = (c_int * len(STAGE_NAMES))()
+    call("ksp_profile_read", ms, n, len(STAGE_NAMES))
+    return {name: (ms[i], n[i]) for i, name in enumerate(STAGE_NAMES)}
 
 
 def default_abs_mode() -> int:

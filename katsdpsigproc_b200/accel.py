@@ -431,6 +431,7 @@ class Dimension:
     """
 
     ALIGN_BYTES = 128
+    _is_power2 = staticmethod(_is_power2)
 
     def __init__(self, size: int, min_padded_round: Optional[int] = None,
                  min_padded_size: Optional[int] = None, alignment: int = 1,

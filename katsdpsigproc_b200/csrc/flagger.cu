@@ -93,18 +93,26 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
         const void *vis_c = (const char *) vis + (size_t) b0 * vis_elem;
         const uint8_t *in_fl = input_flags;
         if (p->flag_mode == KSP_FLAGS_FULL) in_fl = input_flags + b0;
+        ksp_profile_begin(KSP_STAGE_BACKGROUND, s);
         int rc = ksp_background_median_filter_t(s, vis_c, dev_t, in_fl, p->channels, nb,
                                                 p->vis_stride, l.dev_stride, p->input_flags_stride,
                                                 p->width, p->is_amplitude, p->flag_mode,
                                                 p->abs_mode);
+        ksp_profile_end(KSP_STAGE_BACKGROUND, s);
         if (rc) return rc;
+        ksp_profile_begin(KSP_STAGE_NOISE, s);
         rc = ksp_madnz_t(s, dev_t, noise + b0, p->channels, nb, l.dev_stride);
+        ksp_profile_end(KSP_STAGE_NOISE, s);
         if (rc) return rc;
+        ksp_profile_begin(KSP_STAGE_THRESHOLD, s);
         rc = ksp_threshold_sum_packed(s, dev_t, noise + b0, bits_t, p->channels, nb, l.dev_stride,
                                       l.words_stride, p->n_windows, p->n_sigma, p->scales);
+        ksp_profile_end(KSP_STAGE_THRESHOLD, s);
         if (rc) return rc;
+        ksp_profile_begin(KSP_STAGE_EXPAND, s);
         rc = ksp_expand_flags(s, bits_t, flags + b0, p->channels, nb, l.words_stride,
                               p->flags_stride, p->flag_value);
+        ksp_profile_end(KSP_STAGE_EXPAND, s);
         if (rc) return rc;
     }
     return 0;

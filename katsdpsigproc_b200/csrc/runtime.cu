@@ -181,6 +181,79 @@ int ksp_stream_set_l2_window(void *stream, void *base, size_t bytes, float hit_r
 
 }  // extern "C"
 
+// ---------------------------------------------------------------- launch counter / profiling
+#include <atomic>
+#include <mutex>
+#include <vector>
+
+static std::atomic<unsigned long long> g_launches{0};
+void ksp_count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+namespace {
+struct StageSpan { int stage; cudaEvent_t begin, end; };
+std::atomic<bool> g_profile{false};
+std::mutex g_profile_mutex;
+std::vector<StageSpan> g_spans;
+std::vector<cudaEvent_t> g_open(KSP_STAGE_COUNT, nullptr);
+}  // namespace
+
+bool ksp_profile_active() { return g_profile.load(std::memory_order_relaxed); }
+
+void ksp_profile_begin(int stage, cudaStream_t s)
+{
+    if (!ksp_profile_active() || stage < 0 || stage >= KSP_STAGE_COUNT) return;
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    g_open[stage] = e;
+}
+
+void ksp_profile_end(int stage, cudaStream_t s)
+{
+    if (!ksp_profile_active() || stage < 0 || stage >= KSP_STAGE_COUNT) return;
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    if (!g_open[stage]) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, s);
+    g_spans.push_back({stage, g_open[stage], e});
+    g_open[stage] = nullptr;
+}
+
+extern "C" int ksp_kernel_launch_count(unsigned long long *count)
+{
+    if (!count) return KSP_EINVAL;
+    *count = g_launches.load(std::memory_order_relaxed);
+    return 0;
+}
+
+extern "C" int ksp_profile_enable(int on)
+{
+    g_profile.store(on != 0);
+    return 0;
+}
+
+extern "C" int ksp_profile_read(double *stage_ms, int *stage_launches, int n_stages)
+{
+    if (!stage_ms || !stage_launches || n_stages < KSP_STAGE_COUNT) return KSP_EINVAL;
+    std::lock_guard<std::mutex> lock(g_profile_mutex);
+    for (int i = 0; i < n_stages; i++) { stage_ms[i] = 0.0; stage_launches[i] = 0; }
+    int rc = 0;
+    for (const StageSpan &sp : g_spans) {
+        float ms = 0.0f;
+        cudaError_t e = cudaEventSynchronize(sp.end);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, sp.begin, sp.end);
+        if (e != cudaSuccess) rc = (int) e;
+        stage_ms[sp.stage] += ms;
+        stage_launches[sp.stage] += 1;
+        cudaEventDestroy(sp.begin);
+        cudaEventDestroy(sp.end);
+    }
+    g_spans.clear();
+    return rc;
+}
+
 int ksp_sm_count()
 {
     static int cached[64];

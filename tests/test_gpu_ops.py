@@ -1,0 +1,324 @@
+"""Parity through the public Template / Operation API on a real device.
+
+These read like the reference's own device tests (``test/rfi/test_background.py``,
+``test_noise_est.py``, ``test_threshold.py``, ``test_flagger.py``, ``test_percentile.py``,
+``test_transpose.py``, ``test_maskedsum.py``, ``test_accel.py:95-380``): fixed-seed numpy
+input, run through a ``*HostFromDevice`` wrapper or directly bound slots with
+non-trivial padding, compare with the host oracle.
+"""
+
+import numpy as np
+import pytest
+
+from katsdpsigproc_b200 import accel, maskedsum, percentile, transpose
+from katsdpsigproc_b200.accel import DeviceArray, HostArray
+from katsdpsigproc_b200.rfi import device as rfi
+from oracle import contract
+from oracle import host_numpy as hn
+
+pytestmark = pytest.mark.gpu
+
+
+def complex_normal(rs, shape):
+    return (rs.standard_normal(shape) + 1j * rs.standard_normal(shape)).astype(np.complex64)
+
+
+def same_bits(a, b):
+    a, b = np.ascontiguousarray(a, np.float32), np.ascontiguousarray(b, np.float32)
+    return a.shape == b.shape and bool(np.all((a.view(np.uint32) == b.view(np.uint32))
+                                              | (np.isnan(a) & np.isnan(b))))
+
+
+# ----------------------------------------------------------------------------- DeviceArray
+class TestDeviceArray:
+    @pytest.fixture(autouse=True)
+    def setup(self, context, command_queue):
+        self.context, self.queue = context, command_queue
+        self.shape, self.padded = (17, 13), (32, 16)
+        self.array = DeviceArray(context, self.shape, np.int32, self.padded)
+
+    def test_set_get_roundtrip(self):
+        ary = np.random.RandomState(1).randint(0, 100, self.shape).astype(np.int32)
+        self.array.set(self.queue, ary)
+        np.testing.assert_array_equal(ary, self.array.get(self.queue))
+        host = self.array.empty_like()
+        host[...] = ary + 1
+        self.array.set_async(self.queue, host)
+        out = self.array.get_async(self.queue)
+        self.queue.finish()
+        np.testing.assert_array_equal(ary + 1, out)
+        target = self.array.empty_like()
+        assert self.array.get(self.queue, target) is target
+
+    def test_set_rejects_other_dtypes(self):
+        with pytest.raises(TypeError):
+            self.array.set(self.queue, np.zeros(self.shape, np.float32))
+
+    def test_zero(self):
+        self.array.set(self.queue, np.ones(self.shape, np.int32))
+        self.array.zero(self.queue)
+        assert not self.array.get(self.queue).any()
+
+    def test_regions(self):
+        rs = np.random.RandomState(2)
+        src = rs.randint(0, 1000, self.shape).astype(np.int32)
+        self.array.set(self.queue, src)
+        other = DeviceArray(self.context, (9, 20), np.int32, (10, 24))
+        other.zero(self.queue)
+        self.array.copy_region(self.queue, other, np.s_[3:8, 2:12:2], np.s_[1:6, 10:15])
+        expect = np.zeros((9, 20), np.int32)
+        expect[1:6, 10:15] = src[3:8, 2:12:2]
+        np.testing.assert_array_equal(expect, other.get(self.queue))
+
+        host = HostArray((6, 13), np.int32, (8, 16), context=self.context)
+        host[...] = -1
+        self.array.get_region(self.queue, host, np.s_[10:14, 1:], np.s_[2:6, :12])
+        expect_h = np.full((6, 13), -1, np.int32)
+        expect_h[2:6, :12] = src[10:14, 1:]
+        np.testing.assert_array_equal(expect_h, host)
+        with pytest.raises(ValueError):
+            self.array.get_region(self.queue, np.zeros((6, 13), np.int32), np.s_[:6], np.s_[:])
+
+        patch = rs.randint(0, 1000, (4, 5)).astype(np.int32)       # plain array: staged
+        self.array.set_region(self.queue, patch, np.s_[0:4, 8:13], np.s_[:, :])
+        src[0:4, 8:13] = patch
+        np.testing.assert_array_equal(src, self.array.get(self.queue))
+        self.array.set_region(self.queue, host, np.s_[16, :], np.s_[5, :])
+        src[16, :] = host[5, :]
+        np.testing.assert_array_equal(src, self.array.get(self.queue))
+
+    def test_events_time_a_marker_pair(self):
+        start = self.queue.enqueue_marker()
+        self.array.zero(self.queue)
+        end = self.queue.enqueue_marker()
+        assert end.time_since(start) >= 0.0 and start.time_till(end) >= 0.0
+        other = self.context.create_command_queue()
+        other.enqueue_wait_for_events([end])
+        other.finish()
+
+
+# ----------------------------------------------------------------------------- stages
+@pytest.mark.parametrize("width", [5, 13])
+@pytest.mark.parametrize("use_flags", list(rfi.BackgroundFlags))
+@pytest.mark.parametrize("amplitudes", [False, True])
+def test_background(context, command_queue, abs_mode, width, use_flags, amplitudes):
+    rs = np.random.RandomState(1)
+    vis = complex_normal(rs, (417, 313))
+    flags = (rs.random_sample(vis.shape) < 0.1).astype(np.uint8) * 3
+    flags[100:110, :] = 1
+    if amplitudes:
+        vis = np.abs(vis)
+    fl = {rfi.BackgroundFlags.NONE: None, rfi.BackgroundFlags.CHANNEL: flags[:, 0].copy(),
+          rfi.BackgroundFlags.FULL: flags}[use_flags]
+    template = rfi.BackgroundMedianFilterDeviceTemplate(context, width, amplitudes, use_flags,
+                                                        abs_mode=abs_mode)
+    out = rfi.BackgroundHostFromDevice(template, command_queue)(vis, fl)
+    assert same_bits(contract.background(vis, width, fl, amplitudes, abs_mode), out)
+    # the reference's own check: device vs host class to atol 1e-6
+    host = hn.background_median_filter(vis, width, fl, amplitudes)
+    np.testing.assert_allclose(host, out, atol=1e-6)
+    if abs_mode == contract.detect_abs_mode():
+        assert same_bits(host.astype(np.float32), out)
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_noise_est(context, command_queue, transposed):
+    rs = np.random.RandomState(1)
+    deviations = rs.standard_normal((117, 273)).astype(np.float32)
+    template = (rfi.NoiseEstMADTDeviceTemplate(context, 10240) if transposed
+                else rfi.NoiseEstMADDeviceTemplate(context))
+    out = rfi.NoiseEstHostFromDevice(template, command_queue)(deviations)
+    assert same_bits(contract.noise_mad(deviations)[0], out)
+    np.testing.assert_allclose(hn.noise_est_mad(deviations), out, rtol=2e-7)
+
+
+def threshold_case():
+    rs = np.random.RandomState(1)
+    deviations = rs.standard_normal((117, 273)).astype(np.float32) * 10.0
+    spikes = rs.random_sample(deviations.shape) < 0.25
+    deviations[spikes] += 200.0
+    noise = np.linspace(0.0, 50.0, 273).astype(np.float32)
+    return deviations, noise
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_threshold_simple(context, command_queue, transposed):
+    deviations, noise = threshold_case()
+    template = rfi.ThresholdSimpleDeviceTemplate(context, transposed, flag_value=3)
+    out = rfi.ThresholdHostFromDevice(template, command_queue, 11.0)(deviations, noise)
+    np.testing.assert_array_equal(hn.threshold_simple(deviations, noise, 11.0, 3), out)
+
+
+@pytest.mark.parametrize("n_windows", [1, 4, 7])
+def test_threshold_sum(context, command_queue, n_windows):
+    deviations, noise = threshold_case()
+    template = rfi.ThresholdSumDeviceTemplate(context, n_windows=n_windows)
+    out = rfi.ThresholdHostFromDevice(template, command_queue, 11.0, threshold_falloff=1.5)(
+        deviations, noise)
+    near = {}
+    host = hn.threshold_sum(deviations, noise, 11.0, n_windows, 1.5, 1, near)
+    np.testing.assert_array_equal(
+        contract.threshold_sum(deviations, noise, 11.0, n_windows, 1.5), out)
+    assert int((host != out).sum()) <= near.get("band", 0)
+
+
+# ----------------------------------------------------------------------------- flagger
+def flagger_case(channels=117, baselines=131):
+    rs = np.random.RandomState(1)
+    vis = complex_normal(rs, (channels, baselines))
+    spikes = rs.random_sample(vis.shape) < 1 / 16
+    vis += (spikes * (rs.random_sample(vis.shape) * 20 + 50)
+            * np.exp(rs.random_sample(vis.shape) * 2j * np.pi)).astype(np.complex64)
+    input_flags = (rs.random_sample(vis.shape) < 0.05).astype(np.uint8)
+    return vis, spikes, input_flags
+
+
+@pytest.mark.parametrize("noise_t", [False, True])
+@pytest.mark.parametrize("threshold", ["simple", "simple_t", "sum"])
+@pytest.mark.parametrize("use_flags", list(rfi.BackgroundFlags))
+def test_flagger_sequence(context, command_queue, abs_mode, noise_t, threshold, use_flags):
+    """The reference's test matrix (test/rfi/test_flagger.py:74-132): flags == injected spikes."""
+    vis, spikes, input_flags = flagger_case()
+    fl = {rfi.BackgroundFlags.NONE: None, rfi.BackgroundFlags.CHANNEL: input_flags[:, 0].copy(),
+          rfi.BackgroundFlags.FULL: input_flags}[use_flags]
+    background = rfi.BackgroundMedianFilterDeviceTemplate(context, 13, use_flags=use_flags,
+                                                          abs_mode=abs_mode)
+    noise = (rfi.NoiseEstMADTDeviceTemplate(context, 10240) if noise_t
+             else rfi.NoiseEstMADDeviceTemplate(context))
+    thr = {"simple": lambda: rfi.ThresholdSimpleDeviceTemplate(context, False),
+           "simple_t": lambda: rfi.ThresholdSimpleDeviceTemplate(context, True),
+           "sum": lambda: rfi.ThresholdSumDeviceTemplate(context, n_windows=4)}[threshold]()
+    template = rfi.FlaggerDeviceTemplate(background, noise, thr, fused=False)
+    out = rfi.FlaggerHostFromDevice(template, command_queue,
+                                    threshold_args={"n_sigma": 11.0})(vis, fl)
+    expect = spikes.astype(np.uint8)
+    if fl is not None:
+        mask = fl.reshape(-1, 1) if fl.ndim == 1 else fl
+        expect = np.where(mask, 0, expect).astype(np.uint8)
+    if threshold != "sum":
+        np.testing.assert_array_equal(expect, out)
+    want, _, _ = contract.flagger(vis, fl, n_windows=4 if threshold == "sum" else 0,
+                                  abs_mode=abs_mode)
+    np.testing.assert_array_equal(want, out)
+
+
+@pytest.mark.parametrize("use_flags", list(rfi.BackgroundFlags))
+@pytest.mark.parametrize("n_windows", [4, 7])
+def test_flagger_fused_equals_sequence_and_host(context, command_queue, abs_mode, use_flags,
+                                                n_windows):
+    vis, spikes, input_flags = flagger_case(1000, 77)
+    vis[300:330, :] += 2.0          # a broad weak feature for the larger windows
+    fl = {rfi.BackgroundFlags.NONE: None, rfi.BackgroundFlags.CHANNEL: input_flags[:, 0].copy(),
+          rfi.BackgroundFlags.FULL: input_flags}[use_flags]
+
+    def run(fused):
+        template = rfi.FlaggerDeviceTemplate(
+            rfi.BackgroundMedianFilterDeviceTemplate(context, 13, use_flags=use_flags,
+                                                     abs_mode=abs_mode),
+            rfi.NoiseEstMADTDeviceTemplate(context, 10240),
+            rfi.ThresholdSumDeviceTemplate(context, n_windows=n_windows, flag_value=2),
+            fused=fused)
+        fn = template.instantiate(command_queue, *vis.shape, threshold_args={"n_sigma": 7.0})
+        fn.ensure_all_bound()
+        fn.buffer("vis").set(command_queue, vis)
+        if fl is not None:
+            fn.buffer("input_flags").set(command_queue, fl)
+        fn()
+        return fn.buffer("flags").get(command_queue), fn.buffer("noise").get(command_queue), fn
+
+    flags_f, noise_f, fn_f = run(True)
+    flags_s, noise_s, fn_s = run(False)
+    assert fn_f.fused_op is not None and fn_s.fused_op is None
+    np.testing.assert_array_equal(flags_s, flags_f)
+    assert same_bits(noise_s, noise_f)
+    want_flags, want_dev, want_noise = contract.flagger(vis, fl, n_windows=n_windows, n_sigma=7.0,
+                                                        flag_value=2, abs_mode=abs_mode)
+    np.testing.assert_array_equal(want_flags, flags_f)
+    assert same_bits(want_noise, noise_f)
+    assert same_bits(want_dev, fn_s.buffer("deviations").get(command_queue))
+    # and the reference host flagger, with the near-threshold allowance (R6)
+    if abs_mode == contract.detect_abs_mode():
+        near = {}
+        host = hn.flagger(vis, fl, n_sigma=7.0, n_windows=n_windows, flag_value=2, near=near)
+        assert int((host != flags_f).sum()) <= near.get("band", 0)
+
+
+def test_flagger_rebinding_user_buffers(context, command_queue, abs_mode):
+    """Bind caller-owned buffers (allocated to the slots' padded shapes) and run twice."""
+    vis, spikes, _ = flagger_case(256, 40)
+    template = rfi.FlaggerDeviceTemplate(
+        rfi.BackgroundMedianFilterDeviceTemplate(context, 13, abs_mode=abs_mode),
+        rfi.NoiseEstMADTDeviceTemplate(context, 10240),
+        rfi.ThresholdSumDeviceTemplate(context, n_windows=4))
+    fn = template.instantiate(command_queue, 256, 40, threshold_args={"n_sigma": 11.0})
+    slot_v, slot_f = fn.slots["vis"], fn.slots["flags"]
+    mine_v = DeviceArray(context, slot_v.shape, slot_v.dtype, slot_v.required_padded_shape())
+    mine_f = DeviceArray(context, slot_f.shape, slot_f.dtype, slot_f.required_padded_shape())
+    mine_v.set(command_queue, vis)
+    fn(vis=mine_v, flags=mine_f)
+    np.testing.assert_array_equal(spikes.astype(np.uint8), mine_f.get(command_queue))
+    with pytest.raises(ValueError):
+        fn.bind(vis=DeviceArray(context, slot_v.shape, slot_v.dtype, (256, 48)))
+    with pytest.raises(TypeError):
+        fn.bind(vis=DeviceArray(context, slot_v.shape, np.float32, slot_v.required_padded_shape()))
+
+
+# ----------------------------------------------------------------------------- helpers
+@pytest.mark.parametrize("shape", [(4, 5), (53, 7), (53, 81), (32, 64)])
+@pytest.mark.parametrize("dtype,ctype", [(np.float32, "float"), (np.uint8, "unsigned char"),
+                                         (np.complex64, "float2")])
+def test_transpose(context, command_queue, shape, dtype, ctype):
+    template = transpose.TransposeTemplate(context, dtype, ctype)
+    fn = template.instantiate(command_queue, shape)
+    # force non-trivial padding, as the reference's test does (test/test_transpose.py:46-51)
+    fn.slots["src"].dimensions[0].link(accel.Dimension(shape[0], min_padded_round=5))
+    fn.slots["src"].dimensions[1].link(accel.Dimension(shape[1], min_padded_round=7))
+    fn.slots["dest"].dimensions[1].link(accel.Dimension(shape[0], min_padded_round=3))
+    fn.ensure_all_bound()
+    ary = np.random.RandomState(1).uniform(0, 200, shape).astype(dtype)
+    fn.buffer("src").set(command_queue, ary)
+    fn()
+    np.testing.assert_array_equal(ary.T, fn.buffer("dest").get(command_queue))
+
+
+@pytest.mark.parametrize("shape,column_range", [((4096, 1), None), ((4096, 4029), None),
+                                                ((4096, 4030), (8, 4000)), ((27, 301), (0, 301))])
+@pytest.mark.parametrize("is_amplitude", [True, False])
+def test_percentile5(context, command_queue, abs_mode, shape, column_range, is_amplitude):
+    rs = np.random.RandomState(1)
+    rows, cols = min(shape[0], 128), shape[1]
+    src = (np.abs(rs.standard_normal((rows, cols))).astype(np.float32) if is_amplitude
+           else complex_normal(rs, (rows, cols)))
+    template = percentile.Percentile5Template(context, 5000, is_amplitude, abs_mode=abs_mode)
+    fn = template.instantiate(command_queue, (rows, cols), column_range)
+    fn.slots["src"].dimensions[1].link(accel.Dimension(cols, min_padded_round=13))
+    fn.ensure_all_bound()
+    fn.buffer("src").set(command_queue, src)
+    fn()
+    out = fn.buffer("dest").get(command_queue)
+    expected = hn.percentile5(src, column_range)
+    if is_amplitude or abs_mode == contract.detect_abs_mode():
+        assert same_bits(expected, out)
+    else:
+        np.testing.assert_allclose(expected, out, rtol=1e-6)
+
+
+@pytest.mark.parametrize("cols", [2, 4029, 4032])
+@pytest.mark.parametrize("use_amplitudes", [False, True])
+def test_maskedsum(context, command_queue, abs_mode, cols, use_amplitudes):
+    rs = np.random.RandomState(1)
+    rows = 4096
+    src = complex_normal(rs, (rows, cols))
+    mask = np.ones(rows, np.float32)
+    mask[rs.random_sample(rows) < 0.1] = 0
+    template = maskedsum.MaskedSumTemplate(context, use_amplitudes, abs_mode=abs_mode)
+    fn = template.instantiate(command_queue, (rows, cols))
+    fn.ensure_all_bound()
+    fn.buffer("src").set(command_queue, src)
+    fn.buffer("mask").set(command_queue, mask)
+    fn()
+    out = fn.buffer("dest").get(command_queue)
+    data = np.abs(src).astype(np.float64) if use_amplitudes else src.astype(np.complex128)
+    expected = np.sum(data * mask[:, None], axis=0)
+    scale = np.sum(np.abs(src) * mask[:, None], axis=0)
+    assert np.all(np.abs(expected - out) <= 1e-6 * scale)
