@@ -6,22 +6,8 @@
 // the band, flagged / NaN samples skipped, even counts averaged in float64,
 // flagged centre -> 0.
 //
-// Layout and mapping.  vis is channel-major, so one warp reads 32 neighbouring
-// baselines of one channel as a single 256-byte request and every lane walks
-// down the channel axis of its own baseline.  A lane keeps the last 16
-// amplitudes in registers and emits 4 medians per step with a shared selection
-// network (median13.cuh): the 10 samples common to the 4 windows are reduced
-// to their 4 middle ranks once, each output then only merges its 3 private
-// samples (23 min/max per output instead of ~70 for a sort).  Work is split
-// along channels into segments (halo of 12 re-read per segment) so that the
-// grid is several waves of 148 SMs.
-//
-// Slow path (warp-divergent, rare): any of the 16 samples is outside the band,
-// flagged or NaN -> masked median by a small sort (median_masked13).
-//
-// The _t variant stages 32 baselines x 32 channels per warp in shared memory
-// (pitch 36 floats: conflict-free 128-bit writes by lane and 128-bit reads by
-// row) and stores baseline-major rows with 128-bit coalesced stores.
+// Width 13 (the MeerKAT setting) has a dedicated tiled kernel, described at
+// bg13_kernel below; other widths use a simple per-thread ring buffer.
 #include "common.cuh"
 #include "median13.cuh"
 
@@ -33,8 +19,8 @@ constexpr int IN_NUMPY = 0;   // complex64, numpy AVX-512 amplitude rule
 constexpr int IN_HYPOT = 1;   // complex64, correctly rounded hypot
 constexpr int IN_AMP = 2;     // float32 amplitudes
 
-constexpr int BG_THREADS = 128;
-constexpr int TILE_PITCH = 36;
+constexpr int BG_THREADS = 256;
+constexpr int BG_TC = 256;          // channels per tile of the width-13 kernel
 
 struct BgArgs {
     const void *vis;
@@ -79,129 +65,276 @@ __device__ __noinline__ float4 slow_step(const float *e, unsigned bad)
     return make_float4(r[0], r[1], r[2], r[3]);
 }
 
-template <int IN_MODE, int FLAG_MODE, bool TRANSPOSED>
-__global__ void __launch_bounds__(BG_THREADS, 6)
-bg13_kernel(const BgArgs a)
-{
-    __shared__ __align__(16) float tile[TRANSPOSED ? (BG_THREADS / 32) * 32 * TILE_PITCH : 1];
+// ---------------------------------------------------------------- width 13, tiled
+// One block = one tile of 32 baselines x TC channels.
+//
+// Phase 1 (lane <-> baseline): every warp reads groups of 4 consecutive channel rows, 256
+// coalesced bytes of complex64 per row, turns them into amplitudes and stores them
+// baseline-major in shared memory (row pitch P floats, P/4 odd: the 128-bit stores of
+// a warp, one row apart, fall into distinct bank groups).  Unusable samples (outside
+// the band, flagged, NaN amplitude) are stored as NaN.  The tile carries 8 halo
+// channels on the left and 12 on the right so that groups stay 16-byte aligned.
+// Phase 2 (lane <-> run of 4 channels): every thread reads the 20 amplitudes around its 4
+// outputs with 5 conflict-free 128-bit loads, runs the shared selection network
+// (median13.cuh) and stores 4 deviations -- one 128-bit store per thread, 512 contiguous
+// bytes per warp, in the baseline-major (_t) variant; 4 row-strided coalesced stores in
+// the channel-major one.  If the tile holds any unusable sample the threads test their 16
+// window samples first and take the masked slow path where needed.
+constexpr int TILE_B = 32;
+constexpr int HALO_L = 8;            // smem index s = c - c0 + HALO_L
+constexpr int HALO_R = 12;
 
+template <int TC>
+struct TileGeom {
+    static constexpr int P = TC + HALO_L + HALO_R;      // floats per smem row
+    static constexpr int GROUPS = P / 4;
+    static_assert(((P / 4) & 1) == 1, "P/4 must be odd for conflict-free 128-bit row-strided access");
+    static constexpr int SMEM_BYTES = TILE_B * P * 4;
+};
+
+// Phase-1 work of one thread: U groups of 4 consecutive channels (the groups are 32 channels
+// apart) of one baseline -> amplitudes (NaN where unusable) -> one 128-bit shared store per
+// group.  `p` addresses the sample (channel c, this thread's baseline), `fp` its flag;
+// row_bytes / flag_row are the distances to the next channel.  INTERIOR tiles skip every
+// bounds test.  Returns true if some sample is unusable.
+template <int IN_MODE, int FLAG_MODE, bool INTERIOR, int U>
+__device__ __forceinline__ bool amplitudes_to_smem(const char *p, int64_t row_bytes,
+                                                   const uint8_t *fp, int64_t flag_row, int c,
+                                                   int C, float *dst)
+{
+    const float nan = __int_as_float(0x7fc00000);
+    float v[U][4];
+    unsigned usable = 0;                                 // bit 4u+k: sample may be used
+    float2 raw[U][4];
+    // all loads first (predicated at most, no control flow in between), then the arithmetic
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        const char *q = p + (int64_t) (32 * u) * row_bytes;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ck = c + 32 * u + k;
+            const bool in = INTERIOR || (ck >= 0 && ck < C);
+            raw[u][k] = make_float2(1.0f, 0.0f);
+            if (IN_MODE == IN_AMP) {
+                if (in) raw[u][k].x = ldg_stream_f(reinterpret_cast<const float *>(q));
+            } else {
+                if (in) raw[u][k] = ldg_stream_f2(reinterpret_cast<const float2 *>(q));
+            }
+            usable |= (in ? 1u : 0u) << (4 * u + k);
+            q += row_bytes;
+        }
+    }
+    if (FLAG_MODE != KSP_FLAGS_NONE) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint8_t *fq = fp + (int64_t) (32 * u) * flag_row;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if ((usable >> (4 * u + k)) & 1u) {
+                    if (*fq) usable &= ~(1u << (4 * u + k));
+                }
+                fq += flag_row;
+            }
+        }
+    }
+    if (IN_MODE == IN_AMP) {
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[u][k] = raw[u][k].x;
+    } else if (IN_MODE == IN_NUMPY) {
+        unsigned redo = 0;
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                bool ok;
+                v[u][k] = abs_numpy_try(raw[u][k].x, raw[u][k].y, ok);
+                redo |= (ok ? 0u : 1u) << (4 * u + k);
+            }
+        if (redo) {                                      // zeros, denormals, huge, inf, NaN
+#pragma unroll
+            for (int u = 0; u < U; u++)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((redo >> (4 * u + k)) & 1u)
+                        v[u][k] = abs_slow_call(raw[u][k].x, raw[u][k].y, KSP_ABS_NUMPY);
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < U; u++)
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+                v[u][k] = abs_slow_call(raw[u][k].x, raw[u][k].y, KSP_ABS_HYPOT);
+    }
+    bool any_bad = false;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+        if (!(INTERIOR && FLAG_MODE == KSP_FLAGS_NONE)) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) v[u][k] = ((usable >> (4 * u + k)) & 1u) ? v[u][k] : nan;
+        }
+        const float probe = (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
+        any_bad |= (probe != probe);                     // NaN iff some NaN (or inf - inf)
+        *reinterpret_cast<float4 *>(dst + 32 * u) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+    }
+    return any_bad;
+}
+
+template <int IN_MODE, int FLAG_MODE, bool INTERIOR, int TC>
+__device__ __forceinline__ bool tile_phase1(const BgArgs &a, int64_t b0, int c0, float *amp_sm)
+{
+    using G = TileGeom<TC>;
+    constexpr int NWARPS = BG_THREADS / 32;
+    static_assert(NWARPS == 8, "group schedule below assumes 8 warps");
+    constexpr int NEEDED = (TC + HALO_L + 6 + 3) / 4;    // groups that phase 2 reads
+    constexpr int FULL_ITERS = NEEDED / 16;              // 16 groups per block iteration (U = 2)
+    constexpr int REST = NEEDED - 16 * FULL_ITERS;       // < 16, handled with U = 1
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    // a block is 4 warps = 4 channel segments of the same 32 baselines
-    const int64_t b_raw = (int64_t) blockIdx.x * 32 + lane;
-    const bool b_ok = b_raw < a.baselines;
-    const int64_t b = b_ok ? b_raw : a.baselines - 1;
-    const int64_t c_begin = ((int64_t) blockIdx.y * (BG_THREADS / 32) + warp) * a.seg;
-    if (c_begin >= a.channels) return;   // whole warp; no block-level barriers in this kernel
-    const int64_t c_end = min(a.channels, c_begin + (int64_t) a.seg);
-    const int64_t C = a.channels;
+    const int C = (int) a.channels;
+    const int64_t b = min(b0 + lane, a.baselines - 1);   // clamp: duplicates are never stored
+    constexpr int ESZ = (IN_MODE == IN_AMP) ? 4 : 8;
+    const int64_t row_bytes = a.vis_stride * ESZ;
+    int c = c0 - HALO_L + 4 * warp;                       // first channel of this warp's group
+    const char *p = reinterpret_cast<const char *>(a.vis) + ((int64_t) c * a.vis_stride + b) * ESZ;
+    const uint8_t *fp = nullptr;
+    int64_t flag_row = 0;
+    if (FLAG_MODE == KSP_FLAGS_CHANNEL) { fp = a.flags + c; flag_row = 1; }
+    if (FLAG_MODE == KSP_FLAGS_FULL) { fp = a.flags + (int64_t) c * a.flags_stride + b; flag_row = a.flags_stride; }
+    float *dst = amp_sm + lane * G::P + 4 * warp;
+    bool any_bad = false;
+#pragma unroll 1
+    for (int i = 0; i < FULL_ITERS; i++) {
+        any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 2>(p, row_bytes, fp, flag_row,
+                                                                       c, C, dst);
+        p += 64 * row_bytes;
+        fp += 64 * flag_row;
+        c += 64;
+        dst += 64;
+    }
+    if (REST > 8) {
+        if (warp < REST - 8)
+            any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 2>(p, row_bytes, fp,
+                                                                           flag_row, c, C, dst);
+        else
+            any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 1>(p, row_bytes, fp,
+                                                                           flag_row, c, C, dst);
+    } else if (REST > 0) {
+        if (warp < REST)
+            any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 1>(p, row_bytes, fp,
+                                                                           flag_row, c, C, dst);
+    }
+    return any_bad;
+}
 
-    float e[16];
-    unsigned bad = 0;  // logical slot k unusable (outside band / flagged / NaN)
+template <int IN_MODE, int FLAG_MODE, bool TRANSPOSED, int TC>
+__global__ void __launch_bounds__(BG_THREADS, 3)
+bg13_kernel(const BgArgs a)
+{
+    using G = TileGeom<TC>;
+    extern __shared__ __align__(16) float amp_sm[];     // [TILE_B][P]
 
-    // fetch one sample: amplitude + "unusable" bit
-    auto fetch = [&](int64_t c, float &amp) -> unsigned {
-        if (c < 0 || c >= C) {
-            amp = 0.0f;
-            return 1u;
-        }
-        amp = load_amp<IN_MODE>(a.vis, c * a.vis_stride + b);
-        unsigned u = (amp != amp) ? 1u : 0u;
-        if (FLAG_MODE == KSP_FLAGS_CHANNEL) u |= (a.flags[c] != 0);
-        if (FLAG_MODE == KSP_FLAGS_FULL) u |= (a.flags[c * a.flags_stride + b] != 0);
-        return u;
-    };
+    const int64_t b0 = (int64_t) blockIdx.x * TILE_B;
+    const int c0 = (int) blockIdx.y * TC;
+    const int C = (int) a.channels;
+    int tile_bad;
 
-    // prologue: logical slots 0..11 <- channels c_begin-6 .. c_begin+5
+    // ---- phase 1
+    {
+        const bool interior = (c0 - HALO_L >= 0) && (c0 + TC + HALO_R <= C);   // block-uniform
+        bool any_bad;
+        if (interior)
+            any_bad = tile_phase1<IN_MODE, FLAG_MODE, true, TC>(a, b0, c0, amp_sm);
+        else
+            any_bad = tile_phase1<IN_MODE, FLAG_MODE, false, TC>(a, b0, c0, amp_sm);
+        // block-wide: does the tile need the checked path?
+        tile_bad = __syncthreads_or(any_bad);
+    }
+
+    // ---- phase 2, fast: no unusable sample anywhere in the tile
+    if (!tile_bad) {
+        constexpr int RUNS = TC / 4;                 // runs of 4 outputs per baseline row
+        for (int t = threadIdx.x; t < TILE_B * RUNS; t += BG_THREADS) {
+            int bl, j;
+            if (TRANSPOSED) { bl = t / RUNS; j = t % RUNS; }      // lanes walk along channels
+            else            { j = t / TILE_B; bl = t % TILE_B; }  // lanes walk along baselines
+            const float *src = amp_sm + bl * G::P + 4 * j;
+            float w[20];
 #pragma unroll
-    for (int k = 0; k < 12; k++) bad |= fetch(c_begin - 6 + k, e[k]) << k;
-
-    float *my_tile = tile + warp * 32 * TILE_PITCH;
-
-    for (int64_t c16 = c_begin; c16 < c_end; c16 += 16) {
+            for (int k = 0; k < 5; k++) {
+                float4 q = *reinterpret_cast<const float4 *>(src + 4 * k);
+                w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+            }
+            float e[16];
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-            const int rot = 4 * g;  // logical slot k lives in e[(k + rot) & 15]
-            const int64_t c = c16 + 4 * g;
-            if (c < c_end) {  // warp-uniform
-                // new samples: logical slots 12..15 <- channels c+6 .. c+9
-                unsigned nb = 0;
-                if (c + 9 < C && FLAG_MODE == KSP_FLAGS_NONE) {
-                    float s = 0.0f;
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        float v = load_amp<IN_MODE>(a.vis, (c + 6 + k) * a.vis_stride + b);
-                        e[(12 + k + rot) & 15] = v;
-                        s += v;
-                    }
-                    if (s != s) {  // some NaN (or inf - inf): look at each one
-#pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            float v = e[(12 + k + rot) & 15];
-                            nb |= (v != v ? 1u : 0u) << k;
-                        }
-                    }
+            for (int k = 0; k < 16; k++) e[k] = w[k + 2];        // channels c-6 .. c+9
+            float m0, m1, m2, m3;
+            median13x4(e, 0, m0, m1, m2, m3);
+            const float o0 = e[6] - m0, o1 = e[7] - m1, o2 = e[8] - m2, o3 = e[9] - m3;
+            const int c = c0 + 4 * j;
+            const int64_t b = b0 + bl;
+            if (b >= a.baselines || c >= C) continue;
+            if (TRANSPOSED) {
+                float *o = a.out + b * a.out_stride + c;
+                if (c + 3 < C && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    *reinterpret_cast<float4 *>(o) = make_float4(o0, o1, o2, o3);
                 } else {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) nb |= fetch(c + 6 + k, e[(12 + k + rot) & 15]) << k;
-                }
-                bad |= nb << 12;
-
-                float o0, o1, o2, o3;
-                if (bad == 0) {
-                    float m0, m1, m2, m3;
-                    median13x4(e, rot, m0, m1, m2, m3);
-                    o0 = e[(6 + rot) & 15] - m0;
-                    o1 = e[(7 + rot) & 15] - m1;
-                    o2 = e[(8 + rot) & 15] - m2;
-                    o3 = e[(9 + rot) & 15] - m3;
-                } else {
-                    float lin[16];
-#pragma unroll
-                    for (int k = 0; k < 16; k++) lin[k] = e[(k + rot) & 15];
-                    float4 r = slow_step(lin, bad);
-                    o0 = r.x; o1 = r.y; o2 = r.z; o3 = r.w;
-                }
-                bad >>= 4;
-
-                if (TRANSPOSED) {
-                    int col = (int) ((c - c_begin) & 31);
-                    *reinterpret_cast<float4 *>(my_tile + lane * TILE_PITCH + col) =
-                        make_float4(o0, o1, o2, o3);
-                    if (col == 28 || c + 4 >= c_end) {
-                        __syncwarp();
-                        const int64_t tc0 = c - col;            // first channel of the tile
-                        const int64_t tb0 = b_raw - lane;       // first baseline of the tile
-                        const int ncols = (int) min((int64_t) 32, c_end - tc0);
-                        const bool vec = (ncols == 32) && ((a.out_stride & 3) == 0) &&
-                                         ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
-                        if (vec) {
-#pragma unroll
-                            for (int i = 0; i < 8; i++) {
-                                int row = (lane >> 3) + 4 * i;
-                                int cc = 4 * (lane & 7);
-                                float4 v = *reinterpret_cast<const float4 *>(
-                                    my_tile + row * TILE_PITCH + cc);
-                                if (tb0 + row < a.baselines)
-                                    *reinterpret_cast<float4 *>(
-                                        a.out + (tb0 + row) * a.out_stride + tc0 + cc) = v;
-                            }
-                        } else {
-                            for (int row = 0; row < 32; row++) {
-                                if (lane < ncols && tb0 + row < a.baselines)
-                                    a.out[(tb0 + row) * a.out_stride + tc0 + lane] =
-                                        my_tile[row * TILE_PITCH + lane];
-                            }
-                        }
-                        __syncwarp();
-                    }
-                } else if (b_ok) {
-                    float *o = a.out + c * a.out_stride + b;
                     o[0] = o0;
-                    if (c + 1 < c_end) o[a.out_stride] = o1;
-                    if (c + 2 < c_end) o[2 * a.out_stride] = o2;
-                    if (c + 3 < c_end) o[3 * a.out_stride] = o3;
+                    if (c + 1 < C) o[1] = o1;
+                    if (c + 2 < C) o[2] = o2;
+                    if (c + 3 < C) o[3] = o3;
                 }
+            } else {
+                float *o = a.out + c * a.out_stride + b;
+                o[0] = o0;
+                if (c + 1 < C) o[a.out_stride] = o1;
+                if (c + 2 < C) o[2 * a.out_stride] = o2;
+                if (c + 3 < C) o[3 * a.out_stride] = o3;
+            }
+        }
+        return;
+    }
+
+    // ---- phase 2, checked: per-thread test of the 16 window samples
+    {
+        constexpr int RUNS = TC / 4;
+        for (int t = threadIdx.x; t < TILE_B * RUNS; t += BG_THREADS) {
+            int bl, j;
+            if (TRANSPOSED) { bl = t / RUNS; j = t % RUNS; }
+            else            { j = t / TILE_B; bl = t % TILE_B; }
+            const int c = c0 + 4 * j;
+            const int64_t b = b0 + bl;
+            if (b >= a.baselines || c >= C) continue;
+            const float *src = amp_sm + bl * G::P + 4 * j;
+            float e[16];
+            unsigned bad = 0;
+#pragma unroll
+            for (int k = 0; k < 16; k++) {
+                e[k] = src[k + 2];
+                bad |= (e[k] != e[k] ? 1u : 0u) << k;
+            }
+            float o0, o1, o2, o3;
+            if (bad == 0) {
+                float m0, m1, m2, m3;
+                median13x4(e, 0, m0, m1, m2, m3);
+                o0 = e[6] - m0; o1 = e[7] - m1; o2 = e[8] - m2; o3 = e[9] - m3;
+            } else {
+                float4 r = slow_step(e, bad);
+                o0 = r.x; o1 = r.y; o2 = r.z; o3 = r.w;
+            }
+            if (TRANSPOSED) {
+                float *o = a.out + b * a.out_stride + c;
+                o[0] = o0;
+                if (c + 1 < C) o[1] = o1;
+                if (c + 2 < C) o[2] = o2;
+                if (c + 3 < C) o[3] = o3;
+            } else {
+                float *o = a.out + c * a.out_stride + b;
+                o[0] = o0;
+                if (c + 1 < C) o[a.out_stride] = o1;
+                if (c + 2 < C) o[2 * a.out_stride] = o2;
+                if (c + 3 < C) o[3 * a.out_stride] = o3;
             }
         }
     }
@@ -211,7 +344,7 @@ bg13_kernel(const BgArgs a)
 // One thread per (baseline, channel segment); window kept in local memory.
 // Only used when width != 13.
 template <bool TRANSPOSED>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(BG_THREADS)
 bg_generic_kernel(const BgArgs a, int width, int in_mode, int flag_mode)
 {
     const int64_t b = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
@@ -298,6 +431,7 @@ int launch_bg(cudaStream_t s, const void *vis, float *out, const uint8_t *flags,
     if (width > KSP_MAX_WIDTH) return KSP_ETOOLARGE;
     if (flag_mode < KSP_FLAGS_NONE || flag_mode > KSP_FLAGS_FULL) return KSP_EINVAL;
     if (abs_mode != KSP_ABS_NUMPY && abs_mode != KSP_ABS_HYPOT) return KSP_EINVAL;
+    if (channels > 0x7fff0000) return KSP_ETOOLARGE;
     if (channels == 0 || baselines == 0) return 0;
     if (!vis || !out || (flag_mode != KSP_FLAGS_NONE && !flags)) return KSP_EINVAL;
     if (vis_stride < baselines) return KSP_EINVAL;
@@ -310,8 +444,7 @@ int launch_bg(cudaStream_t s, const void *vis, float *out, const uint8_t *flags,
     a.channels = channels; a.baselines = baselines;
     a.vis_stride = vis_stride; a.out_stride = out_stride; a.flags_stride = flags_stride;
     a.seg = pick_segment(channels, baselines);
-    dim3 grid((unsigned) ksp_divup(baselines, 32),
-              (unsigned) ksp_divup(ksp_divup(channels, a.seg), BG_THREADS / 32));
+    dim3 grid((unsigned) ksp_divup(baselines, TILE_B), (unsigned) ksp_divup(channels, BG_TC));
     if (grid.y > 65535) return KSP_ETOOLARGE;
     const int in_mode = is_amplitude ? IN_AMP : (abs_mode == KSP_ABS_NUMPY ? IN_NUMPY : IN_HYPOT);
 
@@ -324,7 +457,8 @@ int launch_bg(cudaStream_t s, const void *vis, float *out, const uint8_t *flags,
     }
 #define KSP_BG_CASE(IM, FM)                                                        \
     if (in_mode == IM && flag_mode == FM) {                                        \
-        bg13_kernel<IM, FM, TRANSPOSED><<<grid, BG_THREADS, 0, s>>>(a);            \
+        bg13_kernel<IM, FM, TRANSPOSED, BG_TC>                                     \
+            <<<grid, BG_THREADS, TileGeom<BG_TC>::SMEM_BYTES, s>>>(a);             \
         KSP_CHECK_LAUNCH();                                                        \
         return 0;                                                                  \
     }

@@ -28,6 +28,7 @@
 // and only the survivors (rare) are evaluated exactly from shared memory.  When
 // a window size > 1 does flag something, the block rebuilds its tree.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -414,13 +415,22 @@ int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise,
 
     int threads, n_chunks;
     const int64_t runs = ksp_divup(channels, RUN);
-    if (runs <= TS_MAX_THREADS) {
+    // Threads per block for long rows.  Blocks of 256 threads (8192-channel spans that overlap
+    // by the reach of the largest window) keep 4 blocks resident per SM, which hides the
+    // barrier and shared-memory latency that a single 1024-thread block per SM exposes.
+    static const int max_threads = [] {
+        const char *e = getenv("KSP_TS_THREADS");
+        int v = e ? atoi(e) : 256;
+        if (v < 32 || v > TS_MAX_THREADS || (v & 31)) v = 256;
+        return v;
+    }();
+    if (runs <= max_threads) {
         threads = (int) (ksp_divup(runs, 32) * 32);
         a.edge = 0;
         a.chunk_valid = threads * RUN;
         n_chunks = 1;
     } else {
-        threads = TS_MAX_THREADS;
+        threads = max_threads;
         const int reach = (1 << n_windows) - n_windows - 1;   // influence radius of a sample
         a.edge = (int) (ksp_divup(reach, RUN) * RUN);
         a.chunk_valid = threads * RUN - 2 * a.edge;

@@ -309,3 +309,29 @@ def test_masked_sum(abs_mode, cols, use_amplitudes):
     data = (np.abs(src).astype(np.float64) if use_amplitudes else src.astype(np.complex128))
     ref = np.sum(data * mask[:, None], axis=0)
     assert np.all(np.abs(ref - out) <= 1e-6 * scale)
+
+
+# ------------------------------------------------------------------ amplitude rule (R1)
+def test_amplitude_rule_wide_range(abs_mode):
+    """A one-row MaskedSum of amplitudes with mask 1 returns the amplitudes themselves, so the
+    kernel's complex absolute value can be compared bit for bit with the oracle's over the
+    whole float range (normal data, huge / tiny exponents, denormals, zeros, inf, NaN)."""
+    rs = np.random.RandomState(77)
+    n = 1 << 20
+    parts = [complex_normal(rs, n)]
+    for lo, hi in ((-149, 128), (-70, -55), (55, 70), (-20, 20)):
+        mag = np.ldexp(rs.uniform(1, 2, (2, n // 4)), rs.randint(lo, hi, (2, n // 4))).astype(np.float32)
+        sign = rs.choice([-1.0, 1.0], (2, n // 4)).astype(np.float32)
+        parts.append((mag[0] * sign[0] + 1j * (mag[1] * sign[1])).astype(np.complex64))
+    special = np.array([0, 1e-45, 1e-38, 1.0, 3e38, np.inf, np.nan, -0.0, 2.0 ** -64, 2.0 ** 64,
+                        2.0 ** -65, 2.0 ** 63, 1.17549435e-38], np.float32)
+    grid = (special[:, None] + 1j * special[None, :]).astype(np.complex64).ravel()
+    parts.append(grid)
+    vis = np.concatenate(parts)[None, :]
+    with np.errstate(all="ignore"):
+        expect = contract.amplitude(vis[0], abs_mode)
+    out = cu.masked_sum(vis, np.ones(1, np.float32), True, abs_mode)
+    assert_same_f32(expect, out)
+    if abs_mode == contract.detect_abs_mode():
+        with np.errstate(all="ignore"):
+            assert_same_f32(np.abs(vis[0]), out)
