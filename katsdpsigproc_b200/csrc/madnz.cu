@@ -14,6 +14,9 @@
 #include "common.cuh"
 #include "select.cuh"
 
+int ksp_row_mad(cudaStream_t s, const float *dev_t, float *noise, int64_t channels,
+                int64_t baselines, int64_t dev_stride);
+
 namespace {
 
 using namespace ksp;
@@ -315,6 +318,8 @@ extern "C" int ksp_madnz_t(void *stream, const float *dev_t, float *noise, int64
     if (!dev_t || !noise) return KSP_EINVAL;
     if (channels > (int64_t) 1 << 30) return KSP_ETOOLARGE;
     cudaStream_t s = (cudaStream_t) stream;
+    if (channels <= 32768)      // row fits one block of the row kernel (threshold.cu / mad.cuh)
+        return ksp_row_mad(s, dev_t, noise, channels, baselines, stride);
     const bool in_smem = channels <= SMEM_KEY_CAP;
     const size_t smem = select_smem_bytes(channels, in_smem);
     if (in_smem) {

@@ -28,6 +28,7 @@
 // and only the survivors (rare) are evaluated exactly from shared memory.  When
 // a window size > 1 does flag something, the block rebuilds its tree.
 #include "common.cuh"
+#include "mad.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -40,9 +41,15 @@ constexpr int TS_MAX_THREADS = 1024;
 constexpr int TS_MAX_WINDOWS = 7;   // windows up to 64 = two runs of reach
 constexpr unsigned FULL = 0xffffffffu;
 
+// MAD_MODE of the row kernel
+constexpr int MAD_NONE = 0;   // thresholds only, noise is an input
+constexpr int MAD_FUSED = 1;  // noise estimate (written to noise_out), then thresholds
+constexpr int MAD_ONLY = 2;   // noise estimate only
+
 struct TsArgs {
     const float *dev_t;
     const float *noise;
+    float *noise_out;
     uint8_t *flags_t;      // byte output (or null)
     uint32_t *bits_t;      // bit-packed output (or null)
     int64_t channels, baselines;
@@ -137,7 +144,7 @@ __device__ __noinline__ uint32_t exact_windows(uint32_t cand, int run_index, int
     return fire;
 }
 
-template <bool PACKED>
+template <bool PACKED, int MAD_MODE>
 __global__ void __launch_bounds__(TS_MAX_THREADS, 1)
 threshold_sum_kernel(const TsArgs a)
 {
@@ -146,41 +153,62 @@ threshold_sum_kernel(const TsArgs a)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int span = T * RUN;
 
+    constexpr int AUX_WORDS = (MAD_MODE != MAD_NONE) ? 2 * MAD_BINS : 33 * RUN;
     float *rowbuf = sm;                                        // T * PITCH
-    float *Dex = rowbuf + T * PITCH;                           // (32 + 1) * RUN
-    uint32_t *Fsm = reinterpret_cast<uint32_t *>(Dex + 33 * RUN);   // T + 2
+    float *Dex = rowbuf + T * PITCH;                           // (32 + 1) * RUN; histograms of the MAD
+    uint32_t *Fsm = reinterpret_cast<uint32_t *>(Dex + AUX_WORDS);  // T + 2
     float *umx = reinterpret_cast<float *>(Fsm + T + 2);       // T + 2
     uint32_t *car1 = reinterpret_cast<uint32_t *>(umx + T + 2);     // T
     uint32_t *car2 = car1 + T;                                 // T
     float *thr = reinterpret_cast<float *>(car2 + T);          // TS_MAX_WINDOWS (+1)
+    uint32_t *mad_misc = reinterpret_cast<uint32_t *>(thr + 8);     // MAD_MISC_WORDS
 
     const int64_t row = blockIdx.x;
-    const int64_t C = a.channels;
-    const int64_t base = (int64_t) blockIdx.y * a.chunk_valid - a.edge;  // global channel of slot 0
+    const int C = (int) a.channels;
+    const int base = (int) blockIdx.y * a.chunk_valid - a.edge;     // row channel of slot 0
     const float *src = a.dev_t + row * a.dev_stride;
 
-    if (tid < a.n_windows)
-        thr[tid] = __double2float_rn((a.n_sigma * (double) a.noise[row]) * a.scales[tid]);
+    if (MAD_MODE == MAD_NONE) {
+        if (tid < a.n_windows)
+            thr[tid] = __double2float_rn((a.n_sigma * (double) a.noise[row]) * a.scales[tid]);
+    } else {
+        uint32_t *h = reinterpret_cast<uint32_t *>(Dex);
+        for (int i = tid; i < 2 * MAD_BINS; i += T) h[i] = 0u;
+        if (tid < 16) mad_misc[tid] = 0u;
+    }
     if (tid < 2) {
         Fsm[T + tid] = 0u;
         umx[T + tid] = -__int_as_float(0x7f800000);
     }
 
-    // ---- stage the chunk: coalesced 128-bit loads -> padded runs
-    const bool vec_ok = ((a.dev_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dev_t) & 15) == 0);
-    for (int q = tid; q < (span >> 2); q += T) {
-        const int p = q << 2;
-        const int64_t g = base + p;
-        float4 v;
-        if (vec_ok && g >= 0 && g + 3 < C) {
-            v = __ldg(reinterpret_cast<const float4 *>(src + g));
-        } else {
-            v.x = (g >= 0 && g < C) ? src[g] : 0.0f;
-            v.y = (g + 1 >= 0 && g + 1 < C) ? src[g + 1] : 0.0f;
-            v.z = (g + 2 >= 0 && g + 2 < C) ? src[g + 2] : 0.0f;
-            v.w = (g + 3 >= 0 && g + 3 < C) ? src[g + 3] : 0.0f;
+    // ---- stage the chunk: coalesced 128-bit loads -> padded runs (zeros outside the band)
+    const bool vec_ok = ((a.dev_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dev_t) & 15) == 0) &&
+                        ((base & 3) == 0);
+    if (vec_ok && base >= 0 && base + span <= C) {
+        // whole span inside the band: no tests, all loads of a thread in flight together
+        const float4 *s4 = reinterpret_cast<const float4 *>(src + base) + tid;
+        float *dst = rowbuf + (tid >> 3) * PITCH + 4 * (tid & 7);
+        const int dstep = (T >> 3) * PITCH;
+#pragma unroll
+        for (int i = 0; i < RUN / 4; i++) {
+            float4 v = __ldg(s4 + i * T);
+            *reinterpret_cast<float4 *>(dst + i * dstep) = v;
         }
-        *reinterpret_cast<float4 *>(rowbuf + p + 4 * (p >> 5)) = v;
+    } else {
+        for (int q = tid; q < (span >> 2); q += T) {
+            const int p = q << 2;
+            const int g = base + p;
+            float4 v;
+            if (vec_ok && g >= 0 && g + 3 < C) {
+                v = __ldg(reinterpret_cast<const float4 *>(src + g));
+            } else {
+                v.x = (g >= 0 && g < C) ? src[g] : 0.0f;
+                v.y = (g + 1 >= 0 && g + 1 < C) ? src[g + 1] : 0.0f;
+                v.z = (g + 2 >= 0 && g + 2 < C) ? src[g + 2] : 0.0f;
+                v.w = (g + 3 >= 0 && g + 3 < C) ? src[g + 3] : 0.0f;
+            }
+            *reinterpret_cast<float4 *>(rowbuf + p + 4 * (p >> 5)) = v;
+        }
     }
     __syncthreads();
 
@@ -192,8 +220,24 @@ threshold_sum_kernel(const TsArgs a)
         float4 v = *reinterpret_cast<const float4 *>(my + 4 * i);
         D[4 * i] = v.x; D[4 * i + 1] = v.y; D[4 * i + 2] = v.z; D[4 * i + 3] = v.w;
     }
-    const int64_t pos0 = base + (int64_t) tid * RUN;            // global channel of D[0]
-    const uint32_t in_range = bit_range(-pos0, C - pos0);
+    const int64_t pos0 = (int64_t) base + (int64_t) tid * RUN;  // row channel of D[0]
+    const uint32_t in_range = bit_range(-pos0, (int64_t) C - pos0);
+
+    if (MAD_MODE != MAD_NONE) {
+        // the block holds the whole row (single chunk): noise estimate first
+        MadScratch sc;
+        sc.hist_a = reinterpret_cast<uint32_t *>(Dex);
+        sc.hist_b = sc.hist_a + MAD_BINS;
+        sc.misc = mad_misc;
+        const float sample = my[(tid * 5 + warp * 3) & 31];
+        const float noise = block_mad_noise(D, sample, sc);
+        if (tid == 0) a.noise_out[row] = noise;
+        if (MAD_MODE == MAD_ONLY) return;
+        __syncthreads();       // the histograms alias Dex
+        if (tid < a.n_windows)
+            thr[tid] = __double2float_rn((a.n_sigma * (double) noise) * a.scales[tid]);
+        __syncthreads();
+    }
 
     // ---- window size 1
     uint32_t F = 0;
@@ -216,7 +260,7 @@ threshold_sum_kernel(const TsArgs a)
     int built = 0;   // D currently holds D_built
     for (int w = 1; w < a.n_windows; w++) {
         const int win = 1 << w;
-        if ((int64_t) win > C) break;
+        if (win > C) break;
         while (built < w) {
             switch (built) {
             case 0: tree_step<0>(D, Dex, lane, warp, nwarps); break;
@@ -230,7 +274,7 @@ threshold_sum_kernel(const TsArgs a)
         }
         const float tw = thr[w];
         // windows that start in my run and lie inside the band
-        const uint32_t valid = bit_range(-pos0, C - (int64_t) win - pos0 + 1);
+        const uint32_t valid = bit_range(-pos0, (int64_t) C - (int64_t) win - pos0 + 1);
         uint32_t fire = 0;
         const float reach_max = fmaxf(um, fmaxf(umx[tid + 1], umx[tid + 2]));
         if (valid != 0u && !(reach_max <= __fmul_rd(tw, 0.99999905f))) {
@@ -291,7 +335,7 @@ threshold_sum_kernel(const TsArgs a)
 
     // ---- write my 32 flags if my run belongs to this chunk's output range
     const int64_t out_lo = (int64_t) blockIdx.y * a.chunk_valid;
-    const int64_t out_hi = min(C, out_lo + (int64_t) a.chunk_valid);
+    const int64_t out_hi = min((int64_t) C, out_lo + (int64_t) a.chunk_valid);
     if (pos0 >= out_lo && pos0 < out_hi) {
         F &= in_range;
         if (PACKED) {
@@ -389,47 +433,74 @@ expand_flags_kernel(const uint32_t *__restrict__ bits_t, uint8_t *__restrict__ f
     }
 }
 
-size_t ts_smem_bytes(int threads)
+size_t ts_smem_bytes(int threads, bool mad)
 {
-    return sizeof(float) * ((size_t) threads * PITCH + 33 * RUN + 4 * ((size_t) threads + 2) + 16);
+    const size_t aux = mad ? 2 * MAD_BINS : 33 * RUN;
+    return sizeof(float) * ((size_t) threads * PITCH + aux + 4 * ((size_t) threads + 2) + 16 +
+                            MAD_MISC_WORDS);
 }
 
-int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise, uint8_t *flags_t,
-                         uint32_t *bits_t, int64_t channels, int64_t baselines, int64_t dev_stride,
-                         int64_t out_stride, int n_windows, double n_sigma, const double *scales,
-                         int flag_value)
+template <bool PACKED, int MAD_MODE>
+int launch_row_kernel(cudaStream_t s, const TsArgs &a, dim3 grid, int threads)
+{
+    const bool mad = MAD_MODE != MAD_NONE;
+    // (per device and cheap, so simply repeated on every launch)
+    KSP_CUDA(cudaFuncSetAttribute(threshold_sum_kernel<PACKED, MAD_MODE>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int) ts_smem_bytes(TS_MAX_THREADS, mad)));
+    threshold_sum_kernel<PACKED, MAD_MODE><<<grid, threads, ts_smem_bytes(threads, mad), s>>>(a);
+    KSP_CHECK_LAUNCH();
+    return 0;
+}
+
+// mad_mode MAD_NONE: thresholds with the given noise.  MAD_FUSED: noise estimate into noise_out,
+// then thresholds.  MAD_ONLY: noise estimate only.  The MAD modes need the whole row in one
+// block: channels <= TS_MAX_THREADS * RUN (KSP_ETOOLARGE otherwise; callers fall back).
+int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise, float *noise_out,
+                         uint8_t *flags_t, uint32_t *bits_t, int64_t channels, int64_t baselines,
+                         int64_t dev_stride, int64_t out_stride, int n_windows, double n_sigma,
+                         const double *scales, int flag_value, int mad_mode)
 {
     if (channels < 0 || baselines < 0 || dev_stride < channels) return KSP_EINVAL;
-    if (n_windows < 1 || !scales) return KSP_EINVAL;
-    if (n_windows > TS_MAX_WINDOWS) return KSP_ETOOLARGE;
-    if (channels == 0 || baselines == 0) return 0;
-    if (!dev_t || !noise || (!flags_t && !bits_t)) return KSP_EINVAL;
+    if (mad_mode != MAD_ONLY) {
+        if (n_windows < 1 || !scales) return KSP_EINVAL;
+        if (n_windows > TS_MAX_WINDOWS) return KSP_ETOOLARGE;
+    }
+    if (channels > 0x7fff0000) return KSP_ETOOLARGE;
+    if (baselines == 0) return 0;
+    if (channels == 0 && mad_mode == MAD_NONE) return 0;
+    if (!dev_t) return KSP_EINVAL;
+    if (mad_mode == MAD_NONE && !noise) return KSP_EINVAL;
+    if (mad_mode != MAD_NONE && !noise_out) return KSP_EINVAL;
+    if (mad_mode != MAD_ONLY && !flags_t && !bits_t) return KSP_EINVAL;
     if (baselines > 0x7fffffff) return KSP_ETOOLARGE;
 
     TsArgs a;
-    a.dev_t = dev_t; a.noise = noise; a.flags_t = flags_t; a.bits_t = bits_t;
+    a.dev_t = dev_t; a.noise = noise; a.noise_out = noise_out; a.flags_t = flags_t; a.bits_t = bits_t;
     a.channels = channels; a.baselines = baselines;
     a.dev_stride = dev_stride; a.out_stride = out_stride;
     a.n_windows = n_windows; a.flag_value = flag_value; a.n_sigma = n_sigma;
-    for (int w = 0; w < TS_MAX_WINDOWS; w++) a.scales[w] = w < n_windows ? scales[w] : 0.0;
+    for (int w = 0; w < TS_MAX_WINDOWS; w++) a.scales[w] = (scales && w < n_windows) ? scales[w] : 0.0;
 
     int threads, n_chunks;
     const int64_t runs = ksp_divup(channels, RUN);
-    // Threads per block for long rows.  Blocks of 256 threads (8192-channel spans that overlap
-    // by the reach of the largest window) keep 4 blocks resident per SM, which hides the
-    // barrier and shared-memory latency that a single 1024-thread block per SM exposes.
-    static const int max_threads = [] {
+    // Threads per block for long rows when only thresholding.  Blocks of fewer threads
+    // (spans that overlap by the reach of the largest window) keep several blocks resident
+    // per SM, which hides barrier and shared-memory latency.
+    static const int chunk_threads = [] {
         const char *e = getenv("KSP_TS_THREADS");
         int v = e ? atoi(e) : 256;
         if (v < 32 || v > TS_MAX_THREADS || (v & 31)) v = 256;
         return v;
     }();
+    const int max_threads = (mad_mode == MAD_NONE) ? chunk_threads : TS_MAX_THREADS;
     if (runs <= max_threads) {
-        threads = (int) (ksp_divup(runs, 32) * 32);
+        threads = (int) (ksp_divup(runs > 0 ? runs : 1, 32) * 32);
         a.edge = 0;
         a.chunk_valid = threads * RUN;
         n_chunks = 1;
     } else {
+        if (mad_mode != MAD_NONE) return KSP_ETOOLARGE;
         threads = max_threads;
         const int reach = (1 << n_windows) - n_windows - 1;   // influence radius of a sample
         a.edge = (int) (ksp_divup(reach, RUN) * RUN);
@@ -437,21 +508,13 @@ int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise,
         n_chunks = (int) ksp_divup(channels, a.chunk_valid);
     }
     if (n_chunks > 65535) return KSP_ETOOLARGE;
-    const size_t smem = ts_smem_bytes(threads);
     dim3 grid((unsigned) baselines, (unsigned) n_chunks);
-    if (bits_t) {
-        KSP_CUDA(cudaFuncSetAttribute(threshold_sum_kernel<true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int) ts_smem_bytes(TS_MAX_THREADS)));
-        threshold_sum_kernel<true><<<grid, threads, smem, s>>>(a);
-    } else {
-        KSP_CUDA(cudaFuncSetAttribute(threshold_sum_kernel<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int) ts_smem_bytes(TS_MAX_THREADS)));
-        threshold_sum_kernel<false><<<grid, threads, smem, s>>>(a);
-    }
-    KSP_CHECK_LAUNCH();
-    return 0;
+    if (mad_mode == MAD_ONLY) return launch_row_kernel<false, MAD_ONLY>(s, a, grid, threads);
+    if (mad_mode == MAD_FUSED)
+        return bits_t ? launch_row_kernel<true, MAD_FUSED>(s, a, grid, threads)
+                      : launch_row_kernel<false, MAD_FUSED>(s, a, grid, threads);
+    return bits_t ? launch_row_kernel<true, MAD_NONE>(s, a, grid, threads)
+                  : launch_row_kernel<false, MAD_NONE>(s, a, grid, threads);
 }
 
 }  // namespace
@@ -462,9 +525,9 @@ extern "C" int ksp_threshold_sum(void *stream, const float *dev_t, const float *
                                  double n_sigma, const double *scales, int flag_value)
 {
     if (flags_stride < channels) return KSP_EINVAL;
-    return launch_threshold_sum((cudaStream_t) stream, dev_t, noise, flags_t, nullptr, channels,
-                                baselines, dev_stride, flags_stride, n_windows, n_sigma, scales,
-                                flag_value);
+    return launch_threshold_sum((cudaStream_t) stream, dev_t, noise, nullptr, flags_t, nullptr,
+                                channels, baselines, dev_stride, flags_stride, n_windows, n_sigma,
+                                scales, flag_value, MAD_NONE);
 }
 
 // internal (fused flagger): bit-packed output, words_stride words per baseline row
@@ -474,8 +537,28 @@ int ksp_threshold_sum_packed(cudaStream_t s, const float *dev_t, const float *no
                              double n_sigma, const double *scales)
 {
     if (words_stride < ksp_divup(channels, 32)) return KSP_EINVAL;
-    return launch_threshold_sum(s, dev_t, noise, nullptr, bits_t, channels, baselines, dev_stride,
-                                words_stride, n_windows, n_sigma, scales, 1);
+    return launch_threshold_sum(s, dev_t, noise, nullptr, nullptr, bits_t, channels, baselines,
+                                dev_stride, words_stride, n_windows, n_sigma, scales, 1, MAD_NONE);
+}
+
+// internal (fused flagger): noise estimate + thresholds in one launch, one block per row.
+// KSP_ETOOLARGE if a row does not fit one block (the caller then uses the separate kernels).
+int ksp_noise_threshold_packed(cudaStream_t s, const float *dev_t, float *noise, uint32_t *bits_t,
+                               int64_t channels, int64_t baselines, int64_t dev_stride,
+                               int64_t words_stride, int n_windows, double n_sigma,
+                               const double *scales)
+{
+    if (words_stride < ksp_divup(channels, 32)) return KSP_EINVAL;
+    return launch_threshold_sum(s, dev_t, nullptr, noise, nullptr, bits_t, channels, baselines,
+                                dev_stride, words_stride, n_windows, n_sigma, scales, 1, MAD_FUSED);
+}
+
+// internal (ksp_madnz_t): noise estimate only, rows of up to TS_MAX_THREADS * RUN channels
+int ksp_row_mad(cudaStream_t s, const float *dev_t, float *noise, int64_t channels,
+                int64_t baselines, int64_t dev_stride)
+{
+    return launch_threshold_sum(s, dev_t, nullptr, noise, nullptr, nullptr, channels, baselines,
+                                dev_stride, 0, 0, 0.0, nullptr, 1, MAD_ONLY);
 }
 
 int ksp_expand_flags(cudaStream_t s, const uint32_t *bits_t, uint8_t *flags, int64_t channels,
