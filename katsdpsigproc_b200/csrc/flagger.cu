@@ -12,6 +12,7 @@
 // written and re-read while still resident in the 126 MB L2 (the scratch is
 // reused chunk after chunk, so its lines are overwritten before eviction).
 #include "common.cuh"
+#include <stdlib.h>
 
 int ksp_threshold_sum_packed(cudaStream_t s, const float *dev_t, const float *noise,
                              uint32_t *bits_t, int64_t channels, int64_t baselines,
@@ -104,11 +105,20 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
                                                 p->abs_mode);
         ksp_profile_end(KSP_STAGE_BACKGROUND, s);
         if (rc) return rc;
-        // noise estimate + thresholds: one launch when a row fits one block, else two
-        ksp_profile_begin(KSP_STAGE_THRESHOLD, s);
-        rc = ksp_noise_threshold_packed(s, dev_t, noise + b0, bits_t, p->channels, nb, l.dev_stride,
-                                        l.words_stride, p->n_windows, p->n_sigma, p->scales);
-        ksp_profile_end(KSP_STAGE_THRESHOLD, s);
+        // noise estimate and thresholds: two small-block kernels by default (several blocks
+        // per SM); KSP_FUSE_ROWS=1 selects the one-block-per-row kernel that does both
+        static const bool fuse_rows = [] {
+            const char *e = getenv("KSP_FUSE_ROWS");
+            return e && atoi(e) != 0;
+        }();
+        rc = KSP_ETOOLARGE;
+        if (fuse_rows) {
+            ksp_profile_begin(KSP_STAGE_THRESHOLD, s);
+            rc = ksp_noise_threshold_packed(s, dev_t, noise + b0, bits_t, p->channels, nb,
+                                            l.dev_stride, l.words_stride, p->n_windows, p->n_sigma,
+                                            p->scales);
+            ksp_profile_end(KSP_STAGE_THRESHOLD, s);
+        }
         if (rc == KSP_ETOOLARGE) {
             ksp_profile_begin(KSP_STAGE_NOISE, s);
             rc = ksp_madnz_t(s, dev_t, noise + b0, p->channels, nb, l.dev_stride);

@@ -14,9 +14,6 @@
 #include "common.cuh"
 #include "select.cuh"
 
-int ksp_row_mad(cudaStream_t s, const float *dev_t, float *noise, int64_t channels,
-                int64_t baselines, int64_t dev_stride);
-
 namespace {
 
 using namespace ksp;
@@ -66,55 +63,264 @@ __device__ void block_median_keys(const KeySource &key_at, int n, uint32_t n_val
     }
 }
 
-template <bool IN_SMEM>
-__global__ void __launch_bounds__(SEL_THREADS, 1)
-madnz_t_kernel(const float *__restrict__ dev_t, float *__restrict__ noise, int channels,
-               int64_t stride)
-{
-    extern __shared__ __align__(16) uint32_t smem[];
-    SelectScratch sc;
-    sc.hist = smem;
-    sc.misc = smem + SELECT_HIST_WORDS;
-    uint32_t *keys = smem + SELECT_HIST_WORDS + 64;
+// ------------------------------------------------------------------ streaming MAD (baseline-major)
+// One block of 256 threads per row, any row length, ~49 KB of shared memory so that four
+// blocks share an SM and hide each other's latency.  The row is streamed from global memory
+// ONCE:
+//   1. bracket [LO, HI] around the median from 1024 samples of the row (32 warp-sorted groups
+//      of 32; LO / HI = medians over the groups of their 44 % / 56 % quantiles);
+//   2. one pass over the row: every thread counts its usable keys and those below LO, and
+//      keeps the ~12 % of its keys that fall inside the bracket in a private list in shared
+//      memory (slot n of thread t at word n * 256 + t: conflict-free, no atomics);
+//   3. select inside the lists: histogram (2048 bins over the bracket), block scan, the 2-3
+//      keys of the wanted bin are sorted by one warp.
+// If the bracket misses the median (~0.2 % of rows), a private list overflows or the wanted
+// bin is crowded (heavy ties), the row is redone with the 4-pass radix select of select.cuh.
+constexpr int MS_THREADS = 256;
+constexpr int MS_SLOTS = 38;              // list slots per thread (mean use ~16 of 128 keys)
+constexpr int MS_BINS = 2048;
+constexpr int MS_SMALL_CAP = 32;
+constexpr uint32_t KEY_INF = 0x7f800000u;
+static_assert(MS_SLOTS * MS_THREADS >= SELECT_HIST_WORDS, "the fallback's histogram aliases the lists");
 
-    const float *row = dev_t + (int64_t) blockIdx.x * stride;
-    const int tid = threadIdx.x;
-    uint32_t valid = 0;
-    const bool vec = ((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(dev_t) & 15) == 0);
-    if (vec) {
-        const float4 *row4 = reinterpret_cast<const float4 *>(row);
-        for (int i = tid; i < (channels >> 2); i += SEL_THREADS) {
-            float4 v = __ldg(row4 + i);
-            uint4 k = make_uint4(mad_key(v.x), mad_key(v.y), mad_key(v.z), mad_key(v.w));
-            valid += (k.x != KEY_SKIP) + (k.y != KEY_SKIP) + (k.z != KEY_SKIP) + (k.w != KEY_SKIP);
-            if (IN_SMEM) reinterpret_cast<uint4 *>(keys)[i] = k;
-        }
-        for (int i = (channels & ~3) + tid; i < channels; i += SEL_THREADS) {
-            uint32_t k = mad_key(row[i]);
-            valid += (k != KEY_SKIP);
-            if (IN_SMEM) keys[i] = k;
-        }
-    } else {
-        for (int i = tid; i < channels; i += SEL_THREADS) {
-            uint32_t k = mad_key(row[i]);
-            valid += (k != KEY_SKIP);
-            if (IN_SMEM) keys[i] = k;
+__device__ __forceinline__ uint32_t sort32(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const uint32_t other = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+            v = keep_min ? min(v, other) : max(v, other);
         }
     }
-    uint32_t n_valid = block_sum<SEL_THREADS>(valid, sc.misc);
-    if (n_valid == 0) {
+    return v;
+}
+
+struct StreamState {
+    uint32_t nv, below, n;   // usable keys, keys below LO, keys kept (may exceed MS_SLOTS)
+    uint32_t *slot;          // next free slot of this thread's list
+};
+
+__device__ __forceinline__ void stream_key(float x, uint32_t lo, uint32_t lo_m1, uint32_t width,
+                                           StreamState &st)
+{
+    const uint32_t key = __float_as_uint(x) & 0x7fffffffu;
+    const uint32_t km1 = key - 1u;                 // zero wraps to the top: never counted
+    st.nv += (km1 < KEY_INF) ? 1u : 0u;
+    st.below += (km1 < lo_m1) ? 1u : 0u;
+    if (key - lo < width) {
+        if (st.n < (uint32_t) MS_SLOTS) *st.slot = key;
+        st.slot += MS_THREADS;
+        st.n++;
+    }
+}
+
+__global__ void __launch_bounds__(MS_THREADS, 4)
+madnz_stream_kernel(const float *__restrict__ dev_t, float *__restrict__ noise, int channels,
+                    int64_t stride)
+{
+    __shared__ __align__(16) uint32_t lists[MS_SLOTS * MS_THREADS];
+    __shared__ __align__(16) uint32_t hist[MS_BINS];
+    __shared__ uint32_t misc[160];
+    // misc: 0 nv, 1 below, 2 overflow flag, 3 bin, 4 count before bin, 5 count in bin, 6 LO,
+    //       7 HI, 8 small count, 9 count <= v1 in lists, 10 min above v1, 11 v1, 12 kept total,
+    //       16..63 scan / fallback scratch, 64..95 group lows, 96..127 group highs,
+    //       128..159 small list
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = MS_THREADS / 32;
+    const float *row = dev_t + (int64_t) blockIdx.x * stride;
+
+    for (int i = tid; i < MS_BINS; i += MS_THREADS) hist[i] = 0u;
+    if (tid < 16) misc[tid] = (tid == 10) ? 0xffffffffu : 0u;
+
+    // ---- 1. bracket
+    {
+        const int step = channels >> 10;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int i = tid * 4 + g;                                   // sample number, 0..1023
+            int pos = (int) (((int64_t) i * channels) >> 10);
+            if (step > 1) pos += (int) (((uint32_t) i * 2654435761u) >> 16) % step;
+            uint32_t key = 0xffffffffu;
+            if (channels > 0) {
+                const uint32_t k = __float_as_uint(row[min(pos, channels - 1)]) & 0x7fffffffu;
+                if ((k - 1u) < KEY_INF) key = k;
+            }
+            // group = the g-th samples of this warp's lanes
+            const bool valid = key != 0xffffffffu;
+            const uint32_t sorted = sort32(key, lane);
+            const int m = __popc(__ballot_sync(0xffffffffu, valid));
+            const uint32_t lo_g = __shfl_sync(0xffffffffu, sorted, (m * 14) >> 5);
+            const uint32_t hi_g = __shfl_sync(0xffffffffu, sorted, min(max(m - 1, 0), (m * 18 + 31) >> 5));
+            if (lane == 0) {
+                misc[64 + warp * 4 + g] = m ? lo_g : 0xffffffffu;
+                misc[96 + warp * 4 + g] = m ? hi_g : 0xffffffffu;
+            }
+        }
+        __syncthreads();
+        if (warp < 2) {
+            const uint32_t v = misc[64 + 32 * warp + lane];
+            const uint32_t s = sort32(v, lane);
+            const int cnt = __popc(__ballot_sync(0xffffffffu, v != 0xffffffffu));
+            const uint32_t pick = __shfl_sync(0xffffffffu, s, warp ? cnt >> 1 : (max(cnt, 1) - 1) >> 1);
+            if (lane == 0) misc[6 + warp] = cnt ? pick : (warp ? KEY_INF : 1u);
+        }
+        __syncthreads();
+    }
+    const uint32_t lo = misc[6];
+    const uint32_t hi = max(misc[7], lo);
+    const uint32_t width = hi - lo + 1u;
+
+    // ---- 2. the one pass over the row
+    uint32_t n_mine;
+    {
+        StreamState st = {0u, 0u, 0u, lists + tid};
+        const uint32_t lo_m1 = lo - 1u;
+        if (((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(dev_t) & 15) == 0)) {
+            const float4 *row4 = reinterpret_cast<const float4 *>(row);
+            const int n4 = channels >> 2;
+            int i = tid;
+            for (; i + 3 * MS_THREADS < n4; i += 4 * MS_THREADS) {
+                float4 v[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) v[u] = __ldg(row4 + i + u * MS_THREADS);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    stream_key(v[u].x, lo, lo_m1, width, st);
+                    stream_key(v[u].y, lo, lo_m1, width, st);
+                    stream_key(v[u].z, lo, lo_m1, width, st);
+                    stream_key(v[u].w, lo, lo_m1, width, st);
+                }
+            }
+            for (; i < n4; i += MS_THREADS) {
+                const float4 v = __ldg(row4 + i);
+                stream_key(v.x, lo, lo_m1, width, st);
+                stream_key(v.y, lo, lo_m1, width, st);
+                stream_key(v.z, lo, lo_m1, width, st);
+                stream_key(v.w, lo, lo_m1, width, st);
+            }
+            for (int j = (n4 << 2) + tid; j < channels; j += MS_THREADS)
+                stream_key(row[j], lo, lo_m1, width, st);
+        } else {
+            for (int j = tid; j < channels; j += MS_THREADS) stream_key(row[j], lo, lo_m1, width, st);
+        }
+        n_mine = st.n;
+        const uint32_t nv = __reduce_add_sync(0xffffffffu, st.nv);
+        const uint32_t below = __reduce_add_sync(0xffffffffu, st.below);
+        const uint32_t kept = __reduce_add_sync(0xffffffffu, st.n);
+        const bool over = __any_sync(0xffffffffu, st.n > (uint32_t) MS_SLOTS);
+        if (lane == 0) {
+            atomicAdd(&misc[0], nv);
+            atomicAdd(&misc[1], below);
+            atomicAdd(&misc[12], kept);
+            if (over) misc[2] = 1u;
+        }
+    }
+    __syncthreads();
+    const uint32_t n_valid = misc[0];
+    if (n_valid == 0) {                                       // block-uniform
         if (tid == 0) noise[blockIdx.x] = __int_as_float(0x7fc00000);
         return;
     }
-    uint32_t lo, hi;
-    if (IN_SMEM) {
-        auto src = [keys](int i) { return keys[i]; };
-        block_median_keys<SEL_THREADS>(src, channels, n_valid, sc, lo, hi);
-    } else {
-        auto src = [row](int i) { return mad_key(row[i]); };
-        block_median_keys<SEL_THREADS>(src, channels, n_valid, sc, lo, hi);
+    const uint32_t rank = (n_valid - 1u) >> 1;                // lower median, 0-based
+    const uint32_t r_rel = rank - misc[1];                    // rank inside the lists (wraps if below)
+    bool fallback = (misc[2] != 0u) || (r_rel >= misc[12]);
+    const uint32_t *mine = lists + tid;
+
+    uint32_t v1 = 0, v2 = 0;
+    if (!fallback) {
+        // ---- 3. select rank r_rel among the kept keys
+        const int shift = (width <= (uint32_t) MS_BINS) ? 0 : (32 - __clz(width - 1u)) - 11;
+        for (uint32_t k = 0; k < n_mine; k++)
+            atomicAdd(&hist[(mine[k * MS_THREADS] - lo) >> shift], 1u);
+        __syncthreads();
+        {
+            constexpr int BPT = MS_BINS / MS_THREADS;         // 8 bins per thread
+            uint32_t h[BPT], own = 0;
+#pragma unroll
+            for (int k = 0; k < BPT; k++) {
+                h[k] = hist[tid * BPT + k];
+                own += h[k];
+            }
+            uint32_t incl = own;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) misc[16 + warp] = incl;
+            __syncthreads();
+            const uint32_t w = (lane < NWARPS) ? misc[16 + lane] : 0u;
+            uint32_t cum = __reduce_add_sync(0xffffffffu, lane < warp ? w : 0u) + incl - own;
+            if (r_rel >= cum && r_rel < cum + own) {
+#pragma unroll
+                for (int k = 0; k < BPT; k++) {
+                    if (r_rel >= cum && r_rel < cum + h[k]) {
+                        misc[3] = (uint32_t) (tid * BPT + k);
+                        misc[4] = cum;
+                        misc[5] = h[k];
+                    }
+                    cum += h[k];
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t bin = misc[3], in_bin = misc[5];
+        const uint32_t r_bin = r_rel - misc[4];               // rank inside the bin
+        if (shift == 0) {
+            v1 = lo + bin;
+        } else if (in_bin <= (uint32_t) MS_SMALL_CAP) {
+            for (uint32_t k = 0; k < n_mine; k++) {
+                const uint32_t key = mine[k * MS_THREADS];
+                if (((key - lo) >> shift) == bin) misc[128 + atomicAdd(&misc[8], 1u)] = key;
+            }
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t s = sort32(lane < (int) in_bin ? misc[128 + lane] : 0xffffffffu, lane);
+                const uint32_t pick = __shfl_sync(0xffffffffu, s, (int) r_bin);
+                if (lane == 0) misc[11] = pick;
+            }
+            __syncthreads();
+            v1 = misc[11];
+        } else {
+            fallback = true;                                  // crowded bin: block-uniform
+        }
     }
-    if (tid == 0) noise[blockIdx.x] = mad_finish(lo, hi);
+    if (!fallback) {
+        v2 = v1;
+        if (!(n_valid & 1u)) {
+            // upper median: another copy of v1 if enough keys are <= v1, else the next key up
+            uint32_t le = 0, above = 0xffffffffu;
+            for (uint32_t k = 0; k < n_mine; k++) {
+                const uint32_t key = mine[k * MS_THREADS];
+                le += (key <= v1) ? 1u : 0u;
+                above = min(above, key > v1 ? key : 0xffffffffu);
+            }
+            le = __reduce_add_sync(0xffffffffu, le);
+            above = __reduce_min_sync(0xffffffffu, above);
+            if (lane == 0) {
+                atomicAdd(&misc[9], le);
+                atomicMin(&misc[10], above);
+            }
+            __syncthreads();
+            const uint32_t count_le = misc[1] + misc[9];
+            if (count_le < rank + 2u) {
+                v2 = misc[10];
+                if (v2 == 0xffffffffu) fallback = true;        // next key lies beyond the bracket
+            }
+        }
+    }
+    if (fallback) {
+        // ---- plain radix select over the row in global memory (rare)
+        __syncthreads();
+        SelectScratch sc;
+        sc.hist = lists;
+        sc.misc = misc + 16;
+        auto src = [row](int i) { return mad_key(row[i]); };
+        block_median_keys<MS_THREADS>(src, channels, n_valid, sc, v1, v2);
+    }
+    if (tid == 0) noise[blockIdx.x] = mad_finish(v1, v2);
 }
 
 // ------------------------------------------------------------------ channel-major MAD
@@ -316,23 +522,9 @@ extern "C" int ksp_madnz_t(void *stream, const float *dev_t, float *noise, int64
     if (channels < 0 || baselines < 0 || stride < channels) return KSP_EINVAL;
     if (baselines == 0) return 0;
     if (!dev_t || !noise) return KSP_EINVAL;
-    if (channels > (int64_t) 1 << 30) return KSP_ETOOLARGE;
-    cudaStream_t s = (cudaStream_t) stream;
-    if (channels <= 32768)      // row fits one block of the row kernel (threshold.cu / mad.cuh)
-        return ksp_row_mad(s, dev_t, noise, channels, baselines, stride);
-    const bool in_smem = channels <= SMEM_KEY_CAP;
-    const size_t smem = select_smem_bytes(channels, in_smem);
-    if (in_smem) {
-        KSP_CUDA(cudaFuncSetAttribute(madnz_t_kernel<true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        madnz_t_kernel<true><<<(unsigned) baselines, SEL_THREADS, smem, s>>>(dev_t, noise,
-                                                                             (int) channels, stride);
-    } else {
-        KSP_CUDA(cudaFuncSetAttribute(madnz_t_kernel<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        madnz_t_kernel<false><<<(unsigned) baselines, SEL_THREADS, smem, s>>>(
-            dev_t, noise, (int) channels, stride);
-    }
+    if (channels > (int64_t) 1 << 30 || baselines > 0x7fffffff) return KSP_ETOOLARGE;
+    madnz_stream_kernel<<<(unsigned) baselines, MS_THREADS, 0, (cudaStream_t) stream>>>(
+        dev_t, noise, (int) channels, stride);
     KSP_CHECK_LAUNCH();
     return 0;
 }
