@@ -42,12 +42,13 @@ Layout make_layout(const ksp_flagger_params *p)
     const int64_t row_bytes = (l.dev_stride + l.words_stride) * 4;
     int64_t chunk = p->chunk_baselines;
     if (chunk <= 0) {
-        // keep the scratch well inside L2: about a third of it, in whole waves of SMs
-        int64_t budget = (int64_t) ksp_l2_bytes() / 3;
-        if (budget < (8 << 20)) budget = 8 << 20;
-        chunk = budget / (row_bytes > 0 ? row_bytes : 1);
-        const int64_t sms = ksp_sm_count();
-        if (chunk >= 2 * sms) chunk = (chunk / sms) * sms;
+        // Measured on B200 (profiles/): the stages are issue-bound, not HBM-bound, so launch
+        // tails cost more than the L2 misses that large chunks cause; take chunks of 32
+        // baselines per SM (a 0.6 GB scratch at 32768 channels) unless KSP_CHUNK says otherwise.
+        const char *e = getenv("KSP_CHUNK");
+        chunk = e ? atoll(e) : 0;
+        if (chunk <= 0) chunk = 32 * (int64_t) ksp_sm_count();
+        (void) row_bytes;
     }
     chunk = (chunk / 32) * 32;
     if (chunk < 32) chunk = 32;

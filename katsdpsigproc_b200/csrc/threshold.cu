@@ -489,8 +489,8 @@ int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise,
     // per SM, which hides barrier and shared-memory latency.
     static const int chunk_threads = [] {
         const char *e = getenv("KSP_TS_THREADS");
-        int v = e ? atoi(e) : 256;
-        if (v < 32 || v > TS_MAX_THREADS || (v & 31)) v = 256;
+        int v = e ? atoi(e) : 128;
+        if (v < 32 || v > TS_MAX_THREADS || (v & 31)) v = 128;
         return v;
     }();
     const int max_threads = (mad_mode == MAD_NONE) ? chunk_threads : TS_MAX_THREADS;
