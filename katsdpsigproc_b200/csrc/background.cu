@@ -21,6 +21,9 @@ constexpr int IN_AMP = 2;     // float32 amplitudes
 
 constexpr int BG_THREADS = 256;
 constexpr int BG_TC = 256;          // channels per tile of the width-13 kernel
+#ifndef BG_MIN_BLOCKS
+#define BG_MIN_BLOCKS 4
+#endif
 
 struct BgArgs {
     const void *vis;
@@ -229,7 +232,7 @@ __device__ __forceinline__ bool tile_phase1(const BgArgs &a, int64_t b0, int c0,
 }
 
 template <int IN_MODE, int FLAG_MODE, bool TRANSPOSED, int TC>
-__global__ void __launch_bounds__(BG_THREADS, 3)
+__global__ void __launch_bounds__(BG_THREADS, BG_MIN_BLOCKS)
 bg13_kernel(const BgArgs a)
 {
     using G = TileGeom<TC>;

@@ -18,10 +18,6 @@ int ksp_threshold_sum_packed(cudaStream_t s, const float *dev_t, const float *no
                              uint32_t *bits_t, int64_t channels, int64_t baselines,
                              int64_t dev_stride, int64_t words_stride, int n_windows,
                              double n_sigma, const double *scales);
-int ksp_noise_threshold_packed(cudaStream_t s, const float *dev_t, float *noise, uint32_t *bits_t,
-                               int64_t channels, int64_t baselines, int64_t dev_stride,
-                               int64_t words_stride, int n_windows, double n_sigma,
-                               const double *scales);
 int ksp_expand_flags(cudaStream_t s, const uint32_t *bits_t, uint8_t *flags, int64_t channels,
                      int64_t baselines, int64_t words_stride, int64_t flags_stride, int flag_value);
 
@@ -106,31 +102,14 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
                                                 p->abs_mode);
         ksp_profile_end(KSP_STAGE_BACKGROUND, s);
         if (rc) return rc;
-        // noise estimate and thresholds: two small-block kernels by default (several blocks
-        // per SM); KSP_FUSE_ROWS=1 selects the one-block-per-row kernel that does both
-        static const bool fuse_rows = [] {
-            const char *e = getenv("KSP_FUSE_ROWS");
-            return e && atoi(e) != 0;
-        }();
-        rc = KSP_ETOOLARGE;
-        if (fuse_rows) {
-            ksp_profile_begin(KSP_STAGE_THRESHOLD, s);
-            rc = ksp_noise_threshold_packed(s, dev_t, noise + b0, bits_t, p->channels, nb,
-                                            l.dev_stride, l.words_stride, p->n_windows, p->n_sigma,
-                                            p->scales);
-            ksp_profile_end(KSP_STAGE_THRESHOLD, s);
-        }
-        if (rc == KSP_ETOOLARGE) {
-            ksp_profile_begin(KSP_STAGE_NOISE, s);
-            rc = ksp_madnz_t(s, dev_t, noise + b0, p->channels, nb, l.dev_stride);
-            ksp_profile_end(KSP_STAGE_NOISE, s);
-            if (rc) return rc;
-            ksp_profile_begin(KSP_STAGE_THRESHOLD, s);
-            rc = ksp_threshold_sum_packed(s, dev_t, noise + b0, bits_t, p->channels, nb,
-                                          l.dev_stride, l.words_stride, p->n_windows, p->n_sigma,
-                                          p->scales);
-            ksp_profile_end(KSP_STAGE_THRESHOLD, s);
-        }
+        ksp_profile_begin(KSP_STAGE_NOISE, s);
+        rc = ksp_madnz_t(s, dev_t, noise + b0, p->channels, nb, l.dev_stride);
+        ksp_profile_end(KSP_STAGE_NOISE, s);
+        if (rc) return rc;
+        ksp_profile_begin(KSP_STAGE_THRESHOLD, s);
+        rc = ksp_threshold_sum_packed(s, dev_t, noise + b0, bits_t, p->channels, nb, l.dev_stride,
+                                      l.words_stride, p->n_windows, p->n_sigma, p->scales);
+        ksp_profile_end(KSP_STAGE_THRESHOLD, s);
         if (rc) return rc;
         ksp_profile_begin(KSP_STAGE_EXPAND, s);
         rc = ksp_expand_flags(s, bits_t, flags + b0, p->channels, nb, l.words_stride,

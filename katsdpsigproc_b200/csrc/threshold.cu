@@ -10,25 +10,32 @@
 //   window i of size 2^w fires  <=>  f64(D_w[i]) > f64(thr_w) * (2^w - #F in it)
 //
 // i.e. the flagged samples (which the reference replaces by thr_w) are moved to
-// the right-hand side exactly, so the tree does not depend on w and is built
-// ONCE for all window sizes as long as no new flags appear (the usual case
-// after the single-sample pass): 1 add + at most 1 compare per sample and
-// window size, instead of w adds + substitution.
+// the right-hand side exactly.
 //
-// Mapping: one block per baseline row (rows up to 32 768 channels; longer rows
-// in overlapping chunks), one thread per run of 32 consecutive channels.  The
-// row is staged once in shared memory with 128-bit coalesced loads (run pitch
-// 36 floats: conflict-free 128-bit reads by run).  Each thread then keeps its
-// 32 partial sums in registers and its 32 flags in one word; a doubling step
-// takes the missing right-hand operands from the next lane with shuffles (the
-// next warp's through a 128-byte shared slot).  Per window size a thread first
-// asks whether any window that touches its run can fire at all:
-//   * no unflagged sample in reach exceeds thr_w            -> nothing can fire
-//   * D_w[i] <= thr_w * (2^w - N_max), N_max = flags in reach -> window i cannot
-// and only the survivors (rare) are evaluated exactly from shared memory.  When
-// a window size > 1 does flag something, the block rebuilds its tree.
+// Almost no window ever fires, so the kernel does not build the trees.  It FILTERS with
+// cheap window sums and evaluates the tree only for the survivors:
+//
+//   * mapping: one thread per run of 32 consecutive channels, one block per span of
+//     T * 32 channels of one baseline (spans overlap by the reach of the largest window,
+//     128 channels, so blocks are independent and small: several per SM);
+//   * every thread keeps the running sums p[k] = u[0] + .. + u[k-1] of its run in registers
+//     and publishes them, its 32 flags, and three statistics of the run (maximum of its
+//     first 8 samples, sum of the positive samples, sum of |u|) in shared memory;
+//   * window size 2^w, thread by thread, cheapest test first:
+//       - sizes 2..8, per group of 8 window starts: no sample of the 16 the group can reach
+//         exceeds thr_w                                  -> none of those windows can fire;
+//       - sizes 16..64: the positive samples within reach add up to less than
+//         thr_w * (2^w - #F within reach)                -> none of the thread's windows can;
+//       - else S~[j] = differences of running sums (own registers + the next one or two runs'
+//         from shared memory); |S~ - D_w| <= E with E = 2.5e-4 * sum|u| within reach
+//         (3 serial sums of 32 terms, the tree's own 6 roundings, with slack), so
+//         S~[j] <= thr_w * (2^w - #F) - E rules the window out;
+//       - survivors (real interference, or decisions within ~1e-4 of the threshold) are
+//         evaluated exactly in tree order from the staged row (exact_windows);
+//   * if a window size flags anything the block dilates the hits over their windows,
+//     rebuilds u and the running sums, and goes on.
+// Non-finite samples make the sums non-finite: every window within reach is then a survivor.
 #include "common.cuh"
-#include "mad.cuh"
 #include <stdlib.h>
 
 namespace {
@@ -36,28 +43,23 @@ namespace {
 using namespace ksp;
 
 constexpr int RUN = 32;
-constexpr int PITCH = 36;
-constexpr int TS_MAX_THREADS = 1024;
-constexpr int TS_MAX_WINDOWS = 7;   // windows up to 64 = two runs of reach
+constexpr int PITCH = 36;            // floats per staged run: 128-bit accesses one run apart are conflict-free
+constexpr int TS_MAX_THREADS = 256;
+constexpr int TS_MAX_WINDOWS = 7;    // windows up to 64 = two runs of reach
 constexpr unsigned FULL = 0xffffffffu;
-
-// MAD_MODE of the row kernel
-constexpr int MAD_NONE = 0;   // thresholds only, noise is an input
-constexpr int MAD_FUSED = 1;  // noise estimate (written to noise_out), then thresholds
-constexpr int MAD_ONLY = 2;   // noise estimate only
+constexpr float FILTER_ERR = 2.5e-4f;
 
 struct TsArgs {
     const float *dev_t;
     const float *noise;
-    float *noise_out;
     uint8_t *flags_t;      // byte output (or null)
     uint32_t *bits_t;      // bit-packed output (or null)
     int64_t channels, baselines;
     int64_t dev_stride, out_stride;   // out_stride: bytes per row, or words per row when packed
     int n_windows;
     int flag_value;
-    int chunk_valid;       // channels produced per chunk (multiple of 32)
-    int edge;              // halo on each side of a chunk (multiple of 32; 0 when 1 chunk)
+    int chunk_valid;       // channels produced per block (multiple of 32)
+    int edge;              // halo on each side of a span (multiple of 32; 0 when one block per row)
     double n_sigma;
     double scales[TS_MAX_WINDOWS];
 };
@@ -72,50 +74,8 @@ __device__ __forceinline__ uint32_t bit_range(int64_t lo, int64_t hi)
     return upto_hi & ~((1u << (int) lo) - 1u);
 }
 
-template <int K>
-__device__ __forceinline__ void tree_step(float (&D)[RUN], float *Dex, int lane, int warp,
-                                          int nwarps)
-{
-    constexpr int S = 1 << K;
-    if (K == 5) {
-        // shift by a whole run: every partial sum needs the same slot of the next thread
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < RUN; i++) Dex[warp * RUN + i] = D[i];
-        }
-        __syncthreads();
-        const bool has_next = warp + 1 < nwarps;
-        const float *nx = Dex + (warp + 1) * RUN;
-#pragma unroll
-        for (int j = 0; j < RUN; j++) {
-            float t = __shfl_down_sync(FULL, D[j], 1);
-            if (lane == 31) t = has_next ? nx[j] : 0.0f;
-            D[j] = D[j] + t;
-        }
-        __syncthreads();
-    } else {
-        float nb[S];
-#pragma unroll
-        for (int i = 0; i < S; i++) nb[i] = __shfl_down_sync(FULL, D[i], 1);
-        if (lane == 0) {
-#pragma unroll
-            for (int i = 0; i < S; i++) Dex[warp * RUN + i] = D[i];
-        }
-        __syncthreads();
-        if (lane == 31) {
-            const bool has_next = warp + 1 < nwarps;
-            const float *nx = Dex + (warp + 1) * RUN;
-#pragma unroll
-            for (int i = 0; i < S; i++) nb[i] = has_next ? nx[i] : 0.0f;
-        }
-#pragma unroll
-        for (int j = 0; j < RUN; j++) D[j] = D[j] + ((j + S < RUN) ? D[j + S] : nb[j + S - RUN]);
-        __syncthreads();
-    }
-}
-
-// Exact evaluation of the candidate windows of one thread (rare, divergent).
-// Rebuilds D_w[i] in the same tree order from the staged row and the published flags.
+// Exact evaluation of the candidate windows of one thread (rare, divergent): D_w[i] in tree
+// order from the staged row and the published flags.
 __device__ __noinline__ uint32_t exact_windows(uint32_t cand, int run_index, int w, float thr_w,
                                                const float *rowbuf, const uint32_t *Fsm, int span)
 {
@@ -144,44 +104,96 @@ __device__ __noinline__ uint32_t exact_windows(uint32_t cand, int run_index, int
     return fire;
 }
 
-template <bool PACKED, int MAD_MODE>
-__global__ void __launch_bounds__(TS_MAX_THREADS, 1)
+// Candidate windows of size W (2..64) that start in this thread's run (rare path).
+//   pb0       published running sums p[1..32] of the own run and, PITCH and 2 * PITCH
+//             floats further on, of the next two runs (shared memory)
+//   F, F1, F2 flag words of the three runs;  tw = thr_w;  err = bound on |S~ - D_w|
+template <int W>
+__device__ __noinline__ uint32_t window_candidates(const float *pb0, uint32_t F, uint32_t F1,
+                                                   uint32_t F2, float tw, float err)
+{
+    const float *pb1 = pb0 + PITCH, *pb2 = pb0 + 2 * PITCH;
+    float p[RUN + 1];
+    p[0] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < RUN / 4; k++) {
+        const float4 q = *reinterpret_cast<const float4 *>(pb0 + 4 * k);
+        p[4 * k + 1] = q.x; p[4 * k + 2] = q.y; p[4 * k + 3] = q.z; p[4 * k + 4] = q.w;
+    }
+    // running sums of the next run that windows of this size can reach: p1[k], k = 1 .. W-1
+    constexpr int NEED1 = (W > RUN) ? RUN : W - 1;
+    float p1[RUN + 1];
+    p1[0] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < (NEED1 + 3) / 4; k++) {
+        const float4 q = *reinterpret_cast<const float4 *>(pb1 + 4 * k);
+        p1[4 * k + 1] = q.x; p1[4 * k + 2] = q.y; p1[4 * k + 3] = q.z; p1[4 * k + 4] = q.w;
+    }
+    float p2[RUN + 1];
+    p2[0] = 0.0f;
+    if (W > RUN) {
+#pragma unroll
+        for (int k = 0; k < RUN / 4; k++) {
+            const float4 q = *reinterpret_cast<const float4 *>(pb2 + 4 * k);
+            p2[4 * k + 1] = q.x; p2[4 * k + 2] = q.y; p2[4 * k + 3] = q.z; p2[4 * k + 4] = q.w;
+        }
+    }
+    const bool any_flag = (F | F1 | F2) != 0u;
+    const float t_full = tw * (float) W;                   // exact: W is a power of two
+    const float slack = err + 1.2e-7f * t_full;            // rounding of tw * (W - n) below
+    uint32_t cand = 0;
+#pragma unroll
+    for (int j = 0; j < RUN; j++) {
+        float s;
+        if (W <= RUN) {
+            if (j + W <= RUN) s = p[j + W] - p[j];
+            else s = (p[RUN] - p[j]) + p1[j + W - RUN];
+        } else {
+            s = ((p[RUN] - p[j]) + p1[RUN]) + p2[j];
+        }
+        float t = t_full;
+        if (any_flag) {
+            int n = __popc(__funnelshift_r(F, F1, j) & ((W >= 32) ? FULL : ((1u << (W & 31)) - 1u)));
+            if (W > RUN) n += __popc(__funnelshift_r(F1, F2, j));
+            t = tw * (float) (W - n);
+        }
+        cand |= (!(s <= t - slack)) ? (1u << j) : 0u;
+    }
+    return cand;
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(TS_MAX_THREADS)
 threshold_sum_kernel(const TsArgs a)
 {
     extern __shared__ __align__(16) float sm[];
     const int T = blockDim.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int tid = threadIdx.x;
     const int span = T * RUN;
+    const float neg_inf = -__int_as_float(0x7f800000);
 
-    constexpr int AUX_WORDS = (MAD_MODE != MAD_NONE) ? 2 * MAD_BINS : 33 * RUN;
-    float *rowbuf = sm;                                        // T * PITCH
-    float *Dex = rowbuf + T * PITCH;                           // (32 + 1) * RUN; histograms of the MAD
-    uint32_t *Fsm = reinterpret_cast<uint32_t *>(Dex + AUX_WORDS);  // T + 2
-    float *umx = reinterpret_cast<float *>(Fsm + T + 2);       // T + 2
-    uint32_t *car1 = reinterpret_cast<uint32_t *>(umx + T + 2);     // T
+    float *rowbuf = sm;                                        // T * PITCH: the staged samples x
+    float *pbuf = rowbuf + T * PITCH;                          // (T + 2) * PITCH: running sums p[1..32]
+    float4 *stat = reinterpret_cast<float4 *>(pbuf + (T + 2) * PITCH);      // T + 2: run statistics
+    uint32_t *Fsm = reinterpret_cast<uint32_t *>(stat + T + 2);             // T + 2
+    uint32_t *car1 = Fsm + T + 2;                              // T
     uint32_t *car2 = car1 + T;                                 // T
     float *thr = reinterpret_cast<float *>(car2 + T);          // TS_MAX_WINDOWS (+1)
-    uint32_t *mad_misc = reinterpret_cast<uint32_t *>(thr + 8);     // MAD_MISC_WORDS
 
     const int64_t row = blockIdx.x;
     const int C = (int) a.channels;
     const int base = (int) blockIdx.y * a.chunk_valid - a.edge;     // row channel of slot 0
     const float *src = a.dev_t + row * a.dev_stride;
 
-    if (MAD_MODE == MAD_NONE) {
-        if (tid < a.n_windows)
-            thr[tid] = __double2float_rn((a.n_sigma * (double) a.noise[row]) * a.scales[tid]);
-    } else {
-        uint32_t *h = reinterpret_cast<uint32_t *>(Dex);
-        for (int i = tid; i < 2 * MAD_BINS; i += T) h[i] = 0u;
-        if (tid < 16) mad_misc[tid] = 0u;
-    }
+    if (tid < a.n_windows)
+        thr[tid] = __double2float_rn((a.n_sigma * (double) a.noise[row]) * a.scales[tid]);
     if (tid < 2) {
         Fsm[T + tid] = 0u;
-        umx[T + tid] = -__int_as_float(0x7f800000);
+        stat[T + tid] = make_float4(neg_inf, 0.0f, 0.0f, 0.0f);
     }
+    for (int i = tid; i < 2 * PITCH; i += T) pbuf[T * PITCH + i] = 0.0f;
 
-    // ---- stage the chunk: coalesced 128-bit loads -> padded runs (zeros outside the band)
+    // ---- stage the span: coalesced 128-bit loads -> padded runs (zeros outside the band)
     const bool vec_ok = ((a.dev_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dev_t) & 15) == 0) &&
                         ((base & 3) == 0);
     if (vec_ok && base >= 0 && base + span <= C) {
@@ -191,110 +203,138 @@ threshold_sum_kernel(const TsArgs a)
         const int dstep = (T >> 3) * PITCH;
 #pragma unroll
         for (int i = 0; i < RUN / 4; i++) {
-            float4 v = __ldg(s4 + i * T);
+            const float4 v = __ldg(s4 + i * T);
             *reinterpret_cast<float4 *>(dst + i * dstep) = v;
         }
+    } else if (vec_ok && (C & 3) == 0) {
+        // span sticks out of the band: whole float4s are either inside or outside
+        float4 v[RUN / 4];
+#pragma unroll
+        for (int i = 0; i < RUN / 4; i++) {
+            const int g = base + 4 * (tid + i * T);
+            v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            if (g >= 0 && g < C) v[i] = __ldg(reinterpret_cast<const float4 *>(src + g));
+        }
+        float *dst = rowbuf + (tid >> 3) * PITCH + 4 * (tid & 7);
+        const int dstep = (T >> 3) * PITCH;
+#pragma unroll
+        for (int i = 0; i < RUN / 4; i++) *reinterpret_cast<float4 *>(dst + i * dstep) = v[i];
     } else {
         for (int q = tid; q < (span >> 2); q += T) {
             const int p = q << 2;
             const int g = base + p;
             float4 v;
-            if (vec_ok && g >= 0 && g + 3 < C) {
-                v = __ldg(reinterpret_cast<const float4 *>(src + g));
-            } else {
-                v.x = (g >= 0 && g < C) ? src[g] : 0.0f;
-                v.y = (g + 1 >= 0 && g + 1 < C) ? src[g + 1] : 0.0f;
-                v.z = (g + 2 >= 0 && g + 2 < C) ? src[g + 2] : 0.0f;
-                v.w = (g + 3 >= 0 && g + 3 < C) ? src[g + 3] : 0.0f;
-            }
+            v.x = (g >= 0 && g < C) ? src[g] : 0.0f;
+            v.y = (g + 1 >= 0 && g + 1 < C) ? src[g + 1] : 0.0f;
+            v.z = (g + 2 >= 0 && g + 2 < C) ? src[g + 2] : 0.0f;
+            v.w = (g + 3 >= 0 && g + 3 < C) ? src[g + 3] : 0.0f;
             *reinterpret_cast<float4 *>(rowbuf + p + 4 * (p >> 5)) = v;
         }
     }
     __syncthreads();
 
-    // ---- my run
-    float D[RUN];
+    // ---- my run: window size 1, then running sums of what is left
     const float *my = rowbuf + tid * PITCH;
-#pragma unroll
-    for (int i = 0; i < RUN / 4; i++) {
-        float4 v = *reinterpret_cast<const float4 *>(my + 4 * i);
-        D[4 * i] = v.x; D[4 * i + 1] = v.y; D[4 * i + 2] = v.z; D[4 * i + 3] = v.w;
-    }
-    const int64_t pos0 = (int64_t) base + (int64_t) tid * RUN;  // row channel of D[0]
+    float *myp = pbuf + tid * PITCH;
+    const int64_t pos0 = (int64_t) base + (int64_t) tid * RUN;  // row channel of element 0
     const uint32_t in_range = bit_range(-pos0, (int64_t) C - pos0);
 
-    if (MAD_MODE != MAD_NONE) {
-        // the block holds the whole row (single chunk): noise estimate first
-        MadScratch sc;
-        sc.hist_a = reinterpret_cast<uint32_t *>(Dex);
-        sc.hist_b = sc.hist_a + MAD_BINS;
-        sc.misc = mad_misc;
-        const float sample = my[(tid * 5 + warp * 3) & 31];
-        const float noise = block_mad_noise(D, sample, sc);
-        if (tid == 0) a.noise_out[row] = noise;
-        if (MAD_MODE == MAD_ONLY) return;
-        __syncthreads();       // the histograms alias Dex
-        if (tid < a.n_windows)
-            thr[tid] = __double2float_rn((a.n_sigma * (double) noise) * a.scales[tid]);
-        __syncthreads();
-    }
-
-    // ---- window size 1
     uint32_t F = 0;
-    float um = -__int_as_float(0x7f800000);
-    {
-        const float t0 = thr[0];
+    float m8[4];        // maxima of u over the four groups of 8 samples
+    float ppos, sabs;   // sum of the positive u, sum of |u|
+    // (re)build u = F ? 0 : x, its running sums and the run statistics; publish them
+    auto rebuild = [&](bool first) {
+        float x[RUN];
 #pragma unroll
-        for (int j = 0; j < RUN; j++) {
-            const bool f = D[j] > t0;
-            F |= f ? (1u << j) : 0u;
-            D[j] = f ? 0.0f : D[j];
-            um = fmaxf(um, D[j]);
+        for (int i = 0; i < RUN / 4; i++) {
+            const float4 v = *reinterpret_cast<const float4 *>(my + 4 * i);
+            x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
         }
-        F &= in_range;
-    }
-    Fsm[tid] = F;
-    umx[tid] = um;
+        if (first) {
+            const float t0 = thr[0];
+#pragma unroll
+            for (int j = 0; j < RUN; j++) F |= (x[j] > t0) ? (1u << j) : 0u;
+            F &= in_range;
+        }
+        sabs = 0.0f;
+        float p[RUN + 1];
+        p[0] = 0.0f;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            float m = neg_inf;
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int j = 8 * g + k;
+                const float u = ((F >> j) & 1u) ? 0.0f : x[j];
+                m = fmaxf(m, u);
+                sabs += fabsf(u);
+                p[j + 1] = p[j] + u;
+            }
+            m8[g] = m;
+        }
+        ppos = 0.5f * (p[RUN] + sabs) * 1.00002f;              // >= sum of max(u, 0), with slack
+#pragma unroll
+        for (int i = 0; i < RUN / 4; i++)
+            *reinterpret_cast<float4 *>(myp + 4 * i) =
+                make_float4(p[4 * i + 1], p[4 * i + 2], p[4 * i + 3], p[4 * i + 4]);
+        Fsm[tid] = F;
+        stat[tid] = make_float4(m8[0], ppos, sabs, 0.0f);
+    };
+    rebuild(true);
     __syncthreads();
 
-    int built = 0;   // D currently holds D_built
+    // runs whose windows of every size lie inside the band need no masks
+    const bool interior = (pos0 >= 0) && (pos0 + RUN + 64 <= (int64_t) C);
+    // neighbours' statistics and flags: reloaded only after a rebuild
+    float4 st1 = stat[tid + 1], st2 = stat[tid + 2];
+    uint32_t F1 = Fsm[tid + 1], F2 = Fsm[tid + 2];
+
     for (int w = 1; w < a.n_windows; w++) {
         const int win = 1 << w;
         if (win > C) break;
-        while (built < w) {
-            switch (built) {
-            case 0: tree_step<0>(D, Dex, lane, warp, nwarps); break;
-            case 1: tree_step<1>(D, Dex, lane, warp, nwarps); break;
-            case 2: tree_step<2>(D, Dex, lane, warp, nwarps); break;
-            case 3: tree_step<3>(D, Dex, lane, warp, nwarps); break;
-            case 4: tree_step<4>(D, Dex, lane, warp, nwarps); break;
-            default: tree_step<5>(D, Dex, lane, warp, nwarps); break;
-            }
-            built++;
-        }
         const float tw = thr[w];
+        if (tw != tw) continue;                                // NaN threshold: nothing can fire
         // windows that start in my run and lie inside the band
-        const uint32_t valid = bit_range(-pos0, (int64_t) C - (int64_t) win - pos0 + 1);
+        const uint32_t valid = interior ? FULL
+                                        : bit_range(-pos0, (int64_t) C - (int64_t) win - pos0 + 1);
         uint32_t fire = 0;
-        const float reach_max = fmaxf(um, fmaxf(umx[tid + 1], umx[tid + 2]));
-        if (valid != 0u && !(reach_max <= __fmul_rd(tw, 0.99999905f))) {
-            const uint32_t F1 = Fsm[tid + 1], F2 = Fsm[tid + 2];
-            const uint32_t m1 = (win > 32) ? FULL : ((1u << (win - 1)) - 1u);
-            const uint32_t m2 = (win > 32) ? 0x7fffffffu : 0u;
-            int nmax = __popc(F) + __popc(F1 & m1) + __popc(F2 & m2);
-            nmax = min(nmax, win);
-            // the bound needs thr_w >= 0; otherwise (negative or NaN) every window is a candidate
-            const float tq = (tw >= 0.0f) ? __double2float_rd((double) tw * (double) (win - nmax))
-                                          : -__int_as_float(0x7f800000);
-            if (!(tw >= 0.0f)) nmax = win;   // force the exact path
-            uint32_t cand = 0;
-#pragma unroll
-            for (int j = 0; j < RUN; j++) cand |= (D[j] > tq) ? (1u << j) : 0u;
-            cand &= valid;
-            if (nmax == 0)
-                fire = cand;
-            else if (cand != 0u)
-                fire = exact_windows(cand, tid, w, tw, rowbuf, Fsm, span);
+        if (valid != 0u) {
+            const bool two = win > RUN;                        // reach covers two more runs
+            // groups of 8 window starts that cannot be ruled out wholesale
+            uint32_t hot = FULL;
+            if (tw >= 0.0f) {
+                if (win <= 8) {
+                    // a window of unflagged samples that are all <= thr_w cannot fire
+                    const float lim = __fmul_rd(tw, 0.99999905f);
+                    hot = 0u;
+                    hot |= !(fmaxf(m8[0], m8[1]) <= lim) ? 0x000000ffu : 0u;
+                    hot |= !(fmaxf(m8[1], m8[2]) <= lim) ? 0x0000ff00u : 0u;
+                    hot |= !(fmaxf(m8[2], m8[3]) <= lim) ? 0x00ff0000u : 0u;
+                    hot |= !(fmaxf(m8[3], st1.x) <= lim) ? 0xff000000u : 0u;
+                } else {
+                    // no window sum exceeds the sum of the positive samples within reach
+                    const float bound = ppos + st1.y + (two ? st2.y : 0.0f);
+                    const int nf = __popc(F) + __popc(F1) + (two ? __popc(F2) : 0);
+                    const float t_min = tw * (float) max(win - nf, 0);
+                    if (bound <= __fmul_rd(t_min, 0.99999f)) hot = 0u;
+                }
+            }
+            hot &= valid;
+            if (hot != 0u) {
+                const float err = FILTER_ERR * ((sabs + st1.z) + (two ? st2.z : 0.0f));
+                const uint32_t G2 = two ? F2 : 0u;
+                uint32_t cand;
+                switch (w) {
+                case 1: cand = window_candidates<2>(myp, F, F1, G2, tw, err); break;
+                case 2: cand = window_candidates<4>(myp, F, F1, G2, tw, err); break;
+                case 3: cand = window_candidates<8>(myp, F, F1, G2, tw, err); break;
+                case 4: cand = window_candidates<16>(myp, F, F1, G2, tw, err); break;
+                case 5: cand = window_candidates<32>(myp, F, F1, G2, tw, err); break;
+                default: cand = window_candidates<64>(myp, F, F1, G2, tw, err); break;
+                }
+                cand &= hot;
+                if (cand != 0u) fire = exact_windows(cand, tid, w, tw, rowbuf, Fsm, span);
+            }
         }
         if (__syncthreads_or(fire != 0u)) {
             // spread every firing window over its 2^w samples (96-bit shift-or)
@@ -313,27 +353,20 @@ threshold_sum_kernel(const TsArgs a)
             car1[tid] = mid;
             car2[tid] = hi;
             __syncthreads();
-            F |= lo | (tid >= 1 ? car1[tid - 1] : 0u) | (tid >= 2 ? car2[tid - 2] : 0u);
-            // rebuild u from the staged row
-            um = -__int_as_float(0x7f800000);
-#pragma unroll
-            for (int i = 0; i < RUN / 4; i++) {
-                float4 v = *reinterpret_cast<const float4 *>(my + 4 * i);
-                D[4 * i] = v.x; D[4 * i + 1] = v.y; D[4 * i + 2] = v.z; D[4 * i + 3] = v.w;
+            const uint32_t Fnew = F | lo | (tid >= 1 ? car1[tid - 1] : 0u) | (tid >= 2 ? car2[tid - 2] : 0u);
+            if (Fnew != F) {
+                F = Fnew;
+                rebuild(false);
             }
-#pragma unroll
-            for (int j = 0; j < RUN; j++) {
-                D[j] = ((F >> j) & 1u) ? 0.0f : D[j];
-                um = fmaxf(um, D[j]);
-            }
-            Fsm[tid] = F;
-            umx[tid] = um;
-            built = 0;
             __syncthreads();
+            st1 = stat[tid + 1];
+            st2 = stat[tid + 2];
+            F1 = Fsm[tid + 1];
+            F2 = Fsm[tid + 2];
         }
     }
 
-    // ---- write my 32 flags if my run belongs to this chunk's output range
+    // ---- write my 32 flags if my run belongs to this block's output range
     const int64_t out_lo = (int64_t) blockIdx.y * a.chunk_valid;
     const int64_t out_hi = min((int64_t) C, out_lo + (int64_t) a.chunk_valid);
     if (pos0 >= out_lo && pos0 < out_hi) {
@@ -415,6 +448,33 @@ expand_flags_kernel(const uint32_t *__restrict__ bits_t, uint8_t *__restrict__ f
     const int64_t b = b0 + 4 * lane;
     const bool vec = (b + 3 < baselines) && ((fstride & 3) == 0) &&
                      ((reinterpret_cast<uintptr_t>(flags) & 3) == 0);
+    if (vec && c_base + 32 <= channels) {
+        // 4 baselines x 4 channels at a time: nibble -> 4 bytes (one multiply), then a 4 x 4
+        // byte transpose with byte permutes gives, per channel, the 4 baselines' flag bytes
+        uint8_t *out = flags + c_base * fstride + b;
+#pragma unroll
+        for (int g = 0; g < 8; g++) {
+            const uint32_t r0 = (((q.x >> (4 * g)) & 0xfu) * 0x00204081u & 0x01010101u) * fv;
+            const uint32_t r1 = (((q.y >> (4 * g)) & 0xfu) * 0x00204081u & 0x01010101u) * fv;
+            const uint32_t r2 = (((q.z >> (4 * g)) & 0xfu) * 0x00204081u & 0x01010101u) * fv;
+            const uint32_t r3 = (((q.w >> (4 * g)) & 0xfu) * 0x00204081u & 0x01010101u) * fv;
+            // r_i: byte k = channel 4g+k of baseline i.  Want t_k: byte i = baseline i of channel 4g+k.
+            const uint32_t a01 = __byte_perm(r0, r1, 0x5140);   // r0.b0 r1.b0 r0.b1 r1.b1
+            const uint32_t b01 = __byte_perm(r0, r1, 0x7362);   // r0.b2 r1.b2 r0.b3 r1.b3
+            const uint32_t a23 = __byte_perm(r2, r3, 0x5140);
+            const uint32_t b23 = __byte_perm(r2, r3, 0x7362);
+            const uint32_t t0 = __byte_perm(a01, a23, 0x5410);  // channel 4g
+            const uint32_t t1 = __byte_perm(a01, a23, 0x7632);  // channel 4g + 1
+            const uint32_t t2 = __byte_perm(b01, b23, 0x5410);  // channel 4g + 2
+            const uint32_t t3 = __byte_perm(b01, b23, 0x7632);  // channel 4g + 3
+            uint8_t *o = out + (int64_t) (4 * g) * fstride;
+            *reinterpret_cast<uint32_t *>(o) = t0;
+            *reinterpret_cast<uint32_t *>(o + fstride) = t1;
+            *reinterpret_cast<uint32_t *>(o + 2 * fstride) = t2;
+            *reinterpret_cast<uint32_t *>(o + 3 * fstride) = t3;
+        }
+        return;
+    }
 #pragma unroll 4
     for (int bit = 0; bit < 32; bit++) {
         const int64_t c = c_base + bit;
@@ -433,88 +493,75 @@ expand_flags_kernel(const uint32_t *__restrict__ bits_t, uint8_t *__restrict__ f
     }
 }
 
-size_t ts_smem_bytes(int threads, bool mad)
+size_t ts_smem_bytes(int threads)
 {
-    const size_t aux = mad ? 2 * MAD_BINS : 33 * RUN;
-    return sizeof(float) * ((size_t) threads * PITCH + aux + 4 * ((size_t) threads + 2) + 16 +
-                            MAD_MISC_WORDS);
+    return sizeof(float) * ((size_t) threads * PITCH + ((size_t) threads + 2) * PITCH +
+                            7 * ((size_t) threads + 2) + 16);
 }
 
-template <bool PACKED, int MAD_MODE>
-int launch_row_kernel(cudaStream_t s, const TsArgs &a, dim3 grid, int threads)
-{
-    const bool mad = MAD_MODE != MAD_NONE;
-    // (per device and cheap, so simply repeated on every launch)
-    KSP_CUDA(cudaFuncSetAttribute(threshold_sum_kernel<PACKED, MAD_MODE>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int) ts_smem_bytes(TS_MAX_THREADS, mad)));
-    threshold_sum_kernel<PACKED, MAD_MODE><<<grid, threads, ts_smem_bytes(threads, mad), s>>>(a);
-    KSP_CHECK_LAUNCH();
-    return 0;
-}
-
-// mad_mode MAD_NONE: thresholds with the given noise.  MAD_FUSED: noise estimate into noise_out,
-// then thresholds.  MAD_ONLY: noise estimate only.  The MAD modes need the whole row in one
-// block: channels <= TS_MAX_THREADS * RUN (KSP_ETOOLARGE otherwise; callers fall back).
-int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise, float *noise_out,
-                         uint8_t *flags_t, uint32_t *bits_t, int64_t channels, int64_t baselines,
-                         int64_t dev_stride, int64_t out_stride, int n_windows, double n_sigma,
-                         const double *scales, int flag_value, int mad_mode)
+int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise, uint8_t *flags_t,
+                         uint32_t *bits_t, int64_t channels, int64_t baselines, int64_t dev_stride,
+                         int64_t out_stride, int n_windows, double n_sigma, const double *scales,
+                         int flag_value)
 {
     if (channels < 0 || baselines < 0 || dev_stride < channels) return KSP_EINVAL;
-    if (mad_mode != MAD_ONLY) {
-        if (n_windows < 1 || !scales) return KSP_EINVAL;
-        if (n_windows > TS_MAX_WINDOWS) return KSP_ETOOLARGE;
-    }
+    if (n_windows < 1 || !scales) return KSP_EINVAL;
+    if (n_windows > TS_MAX_WINDOWS) return KSP_ETOOLARGE;
     if (channels > 0x7fff0000) return KSP_ETOOLARGE;
-    if (baselines == 0) return 0;
-    if (channels == 0 && mad_mode == MAD_NONE) return 0;
-    if (!dev_t) return KSP_EINVAL;
-    if (mad_mode == MAD_NONE && !noise) return KSP_EINVAL;
-    if (mad_mode != MAD_NONE && !noise_out) return KSP_EINVAL;
-    if (mad_mode != MAD_ONLY && !flags_t && !bits_t) return KSP_EINVAL;
+    if (channels == 0 || baselines == 0) return 0;
+    if (!dev_t || !noise || (!flags_t && !bits_t)) return KSP_EINVAL;
     if (baselines > 0x7fffffff) return KSP_ETOOLARGE;
 
     TsArgs a;
-    a.dev_t = dev_t; a.noise = noise; a.noise_out = noise_out; a.flags_t = flags_t; a.bits_t = bits_t;
+    a.dev_t = dev_t; a.noise = noise; a.flags_t = flags_t; a.bits_t = bits_t;
     a.channels = channels; a.baselines = baselines;
     a.dev_stride = dev_stride; a.out_stride = out_stride;
     a.n_windows = n_windows; a.flag_value = flag_value; a.n_sigma = n_sigma;
-    for (int w = 0; w < TS_MAX_WINDOWS; w++) a.scales[w] = (scales && w < n_windows) ? scales[w] : 0.0;
+    for (int w = 0; w < TS_MAX_WINDOWS; w++) a.scales[w] = w < n_windows ? scales[w] : 0.0;
 
-    int threads, n_chunks;
-    const int64_t runs = ksp_divup(channels, RUN);
-    // Threads per block for long rows when only thresholding.  Blocks of fewer threads
-    // (spans that overlap by the reach of the largest window) keep several blocks resident
-    // per SM, which hides barrier and shared-memory latency.
+    // Threads per block for long rows (KSP_TS_THREADS, default 128): spans of 4096 channels
+    // that overlap by the reach of the largest window keep many blocks resident per SM.
     static const int chunk_threads = [] {
         const char *e = getenv("KSP_TS_THREADS");
         int v = e ? atoi(e) : 128;
         if (v < 32 || v > TS_MAX_THREADS || (v & 31)) v = 128;
         return v;
     }();
-    const int max_threads = (mad_mode == MAD_NONE) ? chunk_threads : TS_MAX_THREADS;
-    if (runs <= max_threads) {
-        threads = (int) (ksp_divup(runs > 0 ? runs : 1, 32) * 32);
+    int threads, n_chunks;
+    const int64_t runs = ksp_divup(channels, RUN);
+    if (runs <= chunk_threads) {
+        threads = (int) (ksp_divup(runs, 32) * 32);
         a.edge = 0;
         a.chunk_valid = threads * RUN;
         n_chunks = 1;
     } else {
-        if (mad_mode != MAD_NONE) return KSP_ETOOLARGE;
-        threads = max_threads;
         const int reach = (1 << n_windows) - n_windows - 1;   // influence radius of a sample
         a.edge = (int) (ksp_divup(reach, RUN) * RUN);
+        // balance the spans: as few blocks as chunk_threads allows, equal valid parts
+        const int max_valid = chunk_threads * RUN - 2 * a.edge;
+        if (max_valid < RUN) return KSP_EINVAL;
+        n_chunks = (int) ksp_divup(channels, max_valid);
+        a.chunk_valid = (int) (ksp_divup(ksp_divup(channels, n_chunks), RUN) * RUN);
+        threads = (int) (ksp_divup((a.chunk_valid + 2 * a.edge) / RUN, 32) * 32);
         a.chunk_valid = threads * RUN - 2 * a.edge;
         n_chunks = (int) ksp_divup(channels, a.chunk_valid);
     }
     if (n_chunks > 65535) return KSP_ETOOLARGE;
     dim3 grid((unsigned) baselines, (unsigned) n_chunks);
-    if (mad_mode == MAD_ONLY) return launch_row_kernel<false, MAD_ONLY>(s, a, grid, threads);
-    if (mad_mode == MAD_FUSED)
-        return bits_t ? launch_row_kernel<true, MAD_FUSED>(s, a, grid, threads)
-                      : launch_row_kernel<false, MAD_FUSED>(s, a, grid, threads);
-    return bits_t ? launch_row_kernel<true, MAD_NONE>(s, a, grid, threads)
-                  : launch_row_kernel<false, MAD_NONE>(s, a, grid, threads);
+    const size_t smem = ts_smem_bytes(threads);
+    if (bits_t) {
+        KSP_CUDA(cudaFuncSetAttribute(threshold_sum_kernel<true>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int) ts_smem_bytes(TS_MAX_THREADS)));
+        threshold_sum_kernel<true><<<grid, threads, smem, s>>>(a);
+    } else {
+        KSP_CUDA(cudaFuncSetAttribute(threshold_sum_kernel<false>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int) ts_smem_bytes(TS_MAX_THREADS)));
+        threshold_sum_kernel<false><<<grid, threads, smem, s>>>(a);
+    }
+    KSP_CHECK_LAUNCH();
+    return 0;
 }
 
 }  // namespace
@@ -525,9 +572,9 @@ extern "C" int ksp_threshold_sum(void *stream, const float *dev_t, const float *
                                  double n_sigma, const double *scales, int flag_value)
 {
     if (flags_stride < channels) return KSP_EINVAL;
-    return launch_threshold_sum((cudaStream_t) stream, dev_t, noise, nullptr, flags_t, nullptr,
-                                channels, baselines, dev_stride, flags_stride, n_windows, n_sigma,
-                                scales, flag_value, MAD_NONE);
+    return launch_threshold_sum((cudaStream_t) stream, dev_t, noise, flags_t, nullptr, channels,
+                                baselines, dev_stride, flags_stride, n_windows, n_sigma, scales,
+                                flag_value);
 }
 
 // internal (fused flagger): bit-packed output, words_stride words per baseline row
@@ -537,28 +584,8 @@ int ksp_threshold_sum_packed(cudaStream_t s, const float *dev_t, const float *no
                              double n_sigma, const double *scales)
 {
     if (words_stride < ksp_divup(channels, 32)) return KSP_EINVAL;
-    return launch_threshold_sum(s, dev_t, noise, nullptr, nullptr, bits_t, channels, baselines,
-                                dev_stride, words_stride, n_windows, n_sigma, scales, 1, MAD_NONE);
-}
-
-// internal (fused flagger): noise estimate + thresholds in one launch, one block per row.
-// KSP_ETOOLARGE if a row does not fit one block (the caller then uses the separate kernels).
-int ksp_noise_threshold_packed(cudaStream_t s, const float *dev_t, float *noise, uint32_t *bits_t,
-                               int64_t channels, int64_t baselines, int64_t dev_stride,
-                               int64_t words_stride, int n_windows, double n_sigma,
-                               const double *scales)
-{
-    if (words_stride < ksp_divup(channels, 32)) return KSP_EINVAL;
-    return launch_threshold_sum(s, dev_t, nullptr, noise, nullptr, bits_t, channels, baselines,
-                                dev_stride, words_stride, n_windows, n_sigma, scales, 1, MAD_FUSED);
-}
-
-// internal (ksp_madnz_t): noise estimate only, rows of up to TS_MAX_THREADS * RUN channels
-int ksp_row_mad(cudaStream_t s, const float *dev_t, float *noise, int64_t channels,
-                int64_t baselines, int64_t dev_stride)
-{
-    return launch_threshold_sum(s, dev_t, nullptr, noise, nullptr, nullptr, channels, baselines,
-                                dev_stride, 0, 0, 0.0, nullptr, 1, MAD_ONLY);
+    return launch_threshold_sum(s, dev_t, noise, nullptr, bits_t, channels, baselines, dev_stride,
+                                words_stride, n_windows, n_sigma, scales, 1);
 }
 
 int ksp_expand_flags(cudaStream_t s, const uint32_t *bits_t, uint8_t *flags, int64_t channels,
