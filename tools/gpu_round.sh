@@ -14,13 +14,13 @@ timeout 600 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err
 echo "bench rc=$?"; cat $out/bench_$tag.json; tail -5 $out/bench_$tag.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err
 echo "bench ref rc=$?"; cat $out/bench_ref_$tag.json
-if [ "$2" != "noncu" ]; then
-KREGEX='regex:bg13_kernel|madnz_t_kernel|threshold_sum_kernel|expand_flags_kernel'
+if [ "$2" == "ncuonly" ] || [ "$2" != "noncu" ]; then
+KREGEX='regex:bg13_kernel|madnz_stream_kernel|threshold_sum_kernel|expand_flags_kernel'
 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/plain_$tag.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KREGEX" -c 400 --csv \
     --log-file $out/launches_$tag.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_launches_$tag.log 2>&1
 echo "ncu launches rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k "$KREGEX" -s 120 -c 8 \
+timeout 900 ncu --set full --clock-control none --import-source on -k "$KREGEX" -s 24 -c 8 \
     -f -o $out/prof_$tag python bench.py --steps 2 --warmup 3 --no-cpu-baseline > $out/ncu_full_$tag.log 2>&1
 echo "ncu full rc=$?"; tail -3 $out/ncu_full_$tag.log
 fi
