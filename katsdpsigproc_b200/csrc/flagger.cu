@@ -27,8 +27,38 @@ struct Layout {
     int64_t chunk;        // baselines per chunk (multiple of 32)
     int64_t dev_stride;   // floats per baseline row of dev_t
     int64_t words_stride; // words per baseline row of bits_t
-    size_t dev_bytes, bits_bytes;
+    size_t dev_bytes, bits_bytes;   // per lane
+    int lanes;            // chunks in flight (1 = everything on the caller's stream)
 };
+
+constexpr int MAX_LANES = 4;
+
+// Internal streams and events for running several chunks at a time (per device, created on
+// first use, never destroyed: they live as long as the process).
+struct LanePool {
+    bool ready = false;
+    cudaStream_t stream[MAX_LANES];
+    cudaEvent_t start, done[MAX_LANES];
+};
+
+int get_pool(LanePool **out)
+{
+    static thread_local LanePool pools[64];   // per thread: calls from different threads never share events
+    int dev = 0;
+    KSP_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return KSP_EINVAL;
+    LanePool &pool = pools[dev];
+    if (!pool.ready) {
+        for (int i = 0; i < MAX_LANES; i++) {
+            KSP_CUDA(cudaStreamCreateWithFlags(&pool.stream[i], cudaStreamNonBlocking));
+            KSP_CUDA(cudaEventCreateWithFlags(&pool.done[i], cudaEventDisableTiming));
+        }
+        KSP_CUDA(cudaEventCreateWithFlags(&pool.start, cudaEventDisableTiming));
+        pool.ready = true;
+    }
+    *out = &pool;
+    return 0;
+}
 
 Layout make_layout(const ksp_flagger_params *p)
 {
@@ -36,14 +66,24 @@ Layout make_layout(const ksp_flagger_params *p)
     l.dev_stride = ksp_divup(p->channels, 32) * 32;
     l.words_stride = ksp_divup(ksp_divup(p->channels, 32), 4) * 4;
     const int64_t row_bytes = (l.dev_stride + l.words_stride) * 4;
+    // Chunks in flight ("lanes", KSP_LANES, default 4): consecutive chunks run on separate
+    // internal streams so that the tail of one kernel overlaps the next chunk's kernels.
+    // Measured on B200 (profiles/): the stages are issue-bound rather than HBM-bound and launches
+    // cost ~9 us each, so few large chunks beat many L2-sized ones; the default is one chunk per
+    // lane, at most 32 baselines per SM each (KSP_CHUNK / chunk_baselines override).
+    const char *e = getenv("KSP_LANES");
+    int lanes = e ? atoi(e) : MAX_LANES;
+    if (lanes < 1) lanes = 1;
+    if (lanes > MAX_LANES) lanes = MAX_LANES;
     int64_t chunk = p->chunk_baselines;
     if (chunk <= 0) {
-        // Measured on B200 (profiles/): the stages are issue-bound, not HBM-bound, so launch
-        // tails cost more than the L2 misses that large chunks cause; take chunks of 32
-        // baselines per SM (a 0.6 GB scratch at 32768 channels) unless KSP_CHUNK says otherwise.
-        const char *e = getenv("KSP_CHUNK");
-        chunk = e ? atoll(e) : 0;
-        if (chunk <= 0) chunk = 32 * (int64_t) ksp_sm_count();
+        const char *c = getenv("KSP_CHUNK");
+        chunk = c ? atoll(c) : 0;
+        if (chunk <= 0) {
+            chunk = ksp_divup(ksp_divup(p->baselines, lanes), 32) * 32;
+            const int64_t cap = 32 * (int64_t) ksp_sm_count();
+            if (chunk > cap) chunk = cap;
+        }
         (void) row_bytes;
     }
     chunk = (chunk / 32) * 32;
@@ -53,6 +93,9 @@ Layout make_layout(const ksp_flagger_params *p)
     l.chunk = chunk;
     l.dev_bytes = (size_t) chunk * (size_t) l.dev_stride * 4;
     l.bits_bytes = (size_t) chunk * (size_t) l.words_stride * 4;
+    const int64_t n_chunks = ksp_divup(p->baselines, chunk);
+    if (lanes > n_chunks) lanes = (int) n_chunks;
+    l.lanes = lanes;
     return l;
 }
 
@@ -62,7 +105,7 @@ extern "C" size_t ksp_flagger_scratch_bytes(const ksp_flagger_params *p)
 {
     if (!p || p->channels <= 0 || p->baselines <= 0) return 0;
     Layout l = make_layout(p);
-    return l.dev_bytes + l.bits_bytes;
+    return (l.dev_bytes + l.bits_bytes) * (size_t) l.lanes;
 }
 
 extern "C" int64_t ksp_flagger_chunk_baselines(const ksp_flagger_params *p)
@@ -83,14 +126,29 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
     if (p->flag_mode != KSP_FLAGS_NONE && !input_flags) return KSP_EINVAL;
     if (p->flags_stride < p->baselines || p->vis_stride < p->baselines) return KSP_EINVAL;
     Layout l = make_layout(p);
-    if (scratch_bytes < l.dev_bytes + l.bits_bytes) return KSP_ESCRATCH;
+    const size_t lane_bytes = l.dev_bytes + l.bits_bytes;
+    if (scratch_bytes < lane_bytes * (size_t) l.lanes) return KSP_ESCRATCH;
     if ((uintptr_t) scratch % 16) return KSP_EALIGN;
-    cudaStream_t s = (cudaStream_t) stream;
-    float *dev_t = (float *) scratch;
-    uint32_t *bits_t = (uint32_t *) ((char *) scratch + l.dev_bytes);
+    cudaStream_t user = (cudaStream_t) stream;
     const size_t vis_elem = p->is_amplitude ? 4 : 8;
 
-    for (int64_t b0 = 0; b0 < p->baselines; b0 += l.chunk) {
+    // With several lanes, chunk i runs on internal stream i % lanes with its own scratch; the
+    // internal streams fork from and join back into the caller's stream through events, so
+    // the call keeps plain stream semantics.
+    LanePool *pool = nullptr;
+    if (l.lanes > 1) {
+        int rc = get_pool(&pool);
+        if (rc) return rc;
+        KSP_CUDA(cudaEventRecord(pool->start, user));
+        for (int i = 0; i < l.lanes; i++) KSP_CUDA(cudaStreamWaitEvent(pool->stream[i], pool->start, 0));
+    }
+
+    int64_t index = 0;
+    for (int64_t b0 = 0; b0 < p->baselines; b0 += l.chunk, index++) {
+        const int lane = (int) (index % l.lanes);
+        cudaStream_t s = pool ? pool->stream[lane] : user;
+        float *dev_t = (float *) ((char *) scratch + lane_bytes * (size_t) lane);
+        uint32_t *bits_t = (uint32_t *) ((char *) dev_t + l.dev_bytes);
         const int64_t nb = (p->baselines - b0 < l.chunk) ? p->baselines - b0 : l.chunk;
         const void *vis_c = (const char *) vis + (size_t) b0 * vis_elem;
         const uint8_t *in_fl = input_flags;
@@ -116,6 +174,12 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
                               p->flags_stride, p->flag_value);
         ksp_profile_end(KSP_STAGE_EXPAND, s);
         if (rc) return rc;
+    }
+    if (pool) {
+        for (int i = 0; i < l.lanes; i++) {
+            KSP_CUDA(cudaEventRecord(pool->done[i], pool->stream[i]));
+            KSP_CUDA(cudaStreamWaitEvent(user, pool->done[i], 0));
+        }
     }
     return 0;
 }

@@ -44,7 +44,7 @@ using namespace ksp;
 
 constexpr int RUN = 32;
 constexpr int PITCH = 36;            // floats per staged run: 128-bit accesses one run apart are conflict-free
-constexpr int TS_MAX_THREADS = 256;
+constexpr int TS_MAX_THREADS = 384;
 constexpr int TS_MAX_WINDOWS = 7;    // windows up to 64 = two runs of reach
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float FILTER_ERR = 2.5e-4f;

@@ -40,7 +40,8 @@ def main():
     ap.add_argument("channels", type=int, nargs="?", default=32768)
     ap.add_argument("baselines", type=int, nargs="?", default=8320)
     ap.add_argument("--reps", type=int, default=5)
-    ap.add_argument("--chunks", type=str, default="0,148,296,592")
+    ap.add_argument("--chunks", type=str, default="0")
+    ap.add_argument("--only-fused", action="store_true")
     args = ap.parse_args()
     C, B = args.channels, args.baselines
     dev = torch.device("cuda:0")
@@ -65,28 +66,28 @@ def main():
         res[name] = {"ms": round(ms, 4), "GB/s": round(bytes_per_vis * N / ms / 1e6, 1)}
         print(name, res[name], flush=True)
 
-    rec("background", timeit(lambda: _capi.call(
-        "ksp_background_median_filter", S, p(vis), p(dev_cm), None, C, B, B, B, 0, 13, 0, 0, 0),
-        args.reps, flush), 12)
-    rec("background_t", timeit(lambda: _capi.call(
-        "ksp_background_median_filter_t", S, p(vis), p(dev_t), None, C, B, B, C, 0, 13, 0, 0, 0),
-        args.reps, flush), 12)
-    rec("transpose_f32", timeit(lambda: _capi.call(
-        "ksp_transpose", S, p(dev_t), p(dev_cm), C, B, C, B, 4), args.reps, flush), 8)
-    rec("madnz_t", timeit(lambda: _capi.call(
-        "ksp_madnz_t", S, p(dev_t), p(noise), C, B, C), args.reps, flush), 4)
-    rec("madnz", timeit(lambda: _capi.call(
-        "ksp_madnz", S, p(dev_cm), p(noise), C, B, B), args.reps, flush), 4)
-    rec("threshold_sum7", timeit(lambda: _capi.call(
-        "ksp_threshold_sum", S, p(dev_t), p(noise), p(flags_t), C, B, C, C, 7, c_double(11.0), sc7, 1),
-        args.reps, flush), 5)
-    rec("threshold_simple_t", timeit(lambda: _capi.call(
-        "ksp_threshold_simple", S, p(dev_t), p(noise), p(flags_t), B, C, C, C, c_double(11.0), 1, 1),
-        args.reps, flush), 5)
-    rec("transpose_u8", timeit(lambda: _capi.call(
-        "ksp_transpose", S, p(flags), p(flags_t), B, C, B, C, 1), args.reps, flush), 2)
+    if not args.only_fused:
+        rec("background", timeit(lambda: _capi.call(
+            "ksp_background_median_filter", S, p(vis), p(dev_cm), None, C, B, B, B, 0, 13, 0, 0, 0),
+            args.reps, flush), 12)
+        rec("background_t", timeit(lambda: _capi.call(
+            "ksp_background_median_filter_t", S, p(vis), p(dev_t), None, C, B, B, C, 0, 13, 0, 0, 0),
+            args.reps, flush), 12)
+        rec("transpose_f32", timeit(lambda: _capi.call(
+            "ksp_transpose", S, p(dev_t), p(dev_cm), C, B, C, B, 4), args.reps, flush), 8)
+        rec("madnz_t", timeit(lambda: _capi.call(
+            "ksp_madnz_t", S, p(dev_t), p(noise), C, B, C), args.reps, flush), 4)
+        rec("madnz", timeit(lambda: _capi.call(
+            "ksp_madnz", S, p(dev_cm), p(noise), C, B, B), args.reps, flush), 4)
+        rec("threshold_sum7", timeit(lambda: _capi.call(
+            "ksp_threshold_sum", S, p(dev_t), p(noise), p(flags_t), C, B, C, C, 7, c_double(11.0), sc7, 1),
+            args.reps, flush), 5)
+        rec("threshold_simple_t", timeit(lambda: _capi.call(
+            "ksp_threshold_simple", S, p(dev_t), p(noise), p(flags_t), B, C, C, C, c_double(11.0), 1, 1),
+            args.reps, flush), 5)
+        rec("transpose_u8", timeit(lambda: _capi.call(
+            "ksp_transpose", S, p(flags), p(flags_t), B, C, B, C, 1), args.reps, flush), 2)
     print("flagged fraction", float(flags.float().mean()))
-    del dev_cm, flags_t
     for chunk in [int(x) for x in args.chunks.split(",")]:
         prm = cu.flagger_params(C, B, B, B, n_windows=7, chunk_baselines=chunk)
         nbytes = _capi.load().ksp_flagger_scratch_bytes(byref(prm))
@@ -97,13 +98,14 @@ def main():
             c_size_t(nbytes)), args.reps, flush), 9)
         del scratch
     print("flagged fraction (fused)", float(flags.float().mean()))
-    pct = torch.empty(5, B, dtype=torch.float32, device=dev)
-    rec("percentile5_f32", timeit(lambda: _capi.call(
-        "ksp_percentile5", S, p(dev_t), p(pct), B, C, B, 0, C, 1, 0), args.reps, flush), 4)
-    mask = (torch.rand(C, device=dev) < 0.9).float()
-    dest = torch.empty(B, 2, dtype=torch.float32, device=dev)
-    rec("maskedsum_c64", timeit(lambda: _capi.call(
-        "ksp_maskedsum", S, p(vis), p(mask), p(dest), C, B, B, 0, 0), args.reps, flush), 8)
+    if not args.only_fused:
+        pct = torch.empty(5, B, dtype=torch.float32, device=dev)
+        rec("percentile5_f32", timeit(lambda: _capi.call(
+            "ksp_percentile5", S, p(dev_t), p(pct), B, C, B, 0, C, 1, 0), args.reps, flush), 4)
+        mask = (torch.rand(C, device=dev) < 0.9).float()
+        dest = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        rec("maskedsum_c64", timeit(lambda: _capi.call(
+            "ksp_maskedsum", S, p(vis), p(mask), p(dest), C, B, B, 0, 0), args.reps, flush), 8)
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/time_kernels.json", "w") as f:
         json.dump({"channels": C, "baselines": B, "results": res}, f, indent=1)
