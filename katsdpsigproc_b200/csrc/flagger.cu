@@ -95,6 +95,7 @@ Layout make_layout(const ksp_flagger_params *p)
     l.bits_bytes = (size_t) chunk * (size_t) l.words_stride * 4;
     const int64_t n_chunks = ksp_divup(p->baselines, chunk);
     if (lanes > n_chunks) lanes = (int) n_chunks;
+    if (ksp_profile_active()) lanes = 1;   // stage timing needs the stages one after another
     l.lanes = lanes;
     return l;
 }

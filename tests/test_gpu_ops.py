@@ -322,3 +322,39 @@ def test_maskedsum(context, command_queue, abs_mode, cols, use_amplitudes):
     expected = np.sum(data * mask[:, None], axis=0)
     scale = np.sum(np.abs(src) * mask[:, None], axis=0)
     assert np.all(np.abs(expected - out) <= 1e-6 * scale)
+
+
+# ----------------------------------------------------------------------------- streaming ingest
+@pytest.mark.parametrize("depth", [1, 2, 3])
+@pytest.mark.parametrize("use_flags", [rfi.BackgroundFlags.NONE, rfi.BackgroundFlags.CHANNEL])
+def test_streaming_flagger(context, abs_mode, depth, use_flags):
+    """Dumps go through upload / compute / download queues with `depth` in flight; every
+    result must equal the one-dump-at-a-time oracle, in order."""
+    from katsdpsigproc_b200 import streaming
+
+    channels, baselines = 512, 70
+    template = rfi.FlaggerDeviceTemplate(
+        rfi.BackgroundMedianFilterDeviceTemplate(context, 13, use_flags=use_flags, abs_mode=abs_mode),
+        rfi.NoiseEstMADTDeviceTemplate(context, 10240),
+        rfi.ThresholdSumDeviceTemplate(context, n_windows=7))
+    stream = streaming.StreamingFlagger(template, channels, baselines, depth=depth,
+                                        threshold_args={"n_sigma": 9.0})
+    rs = np.random.RandomState(5)
+    dumps, chan_flags, results = [], [], []
+    for i in range(7):
+        vis = complex_normal(rs, (channels, baselines))
+        spikes = rs.random_sample(vis.shape) < 1 / 32
+        vis += (spikes * 60.0).astype(np.complex64)
+        fl = (rs.random_sample(channels) < 0.05).astype(np.uint8) if use_flags else None
+        dumps.append(vis)
+        chan_flags.append(fl)
+        out = stream.submit(vis, fl)
+        if out is not None:
+            results.append(out.copy())
+    results.extend(out.copy() for out in stream.drain())
+    assert len(results) == len(dumps)
+    for vis, fl, got in zip(dumps, chan_flags, results):
+        want, _, _ = contract.flagger(vis, fl, n_windows=7, n_sigma=9.0, abs_mode=abs_mode)
+        np.testing.assert_array_equal(want, got)
+    with pytest.raises(TypeError):
+        stream.submit(dumps[0], None if use_flags else np.zeros(channels, np.uint8))
