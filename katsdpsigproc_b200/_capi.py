@@ -19,7 +19,9 @@ MAX_WINDOWS = 7
 MAX_WIDTH = 63
 H2D, D2H, D2D = 1, 2, 3
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib", "libksp_b200.so")
+# KSP_B200_LIB points at an alternative build of the library (kernel tuning experiments)
+LIB_PATH = os.environ.get("KSP_B200_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "_lib", "libksp_b200.so")
 
 
 class KspError(RuntimeError):

@@ -20,7 +20,10 @@ constexpr int IN_HYPOT = 1;   // complex64, correctly rounded hypot
 constexpr int IN_AMP = 2;     // float32 amplitudes
 
 constexpr int BG_THREADS = 256;
-constexpr int BG_TC = 256;          // channels per tile of the width-13 kernel
+#ifndef BG_TC_VALUE
+#define BG_TC_VALUE 256
+#endif
+constexpr int BG_TC = BG_TC_VALUE;          // channels per tile of the width-13 kernel
 #ifndef BG_MIN_BLOCKS
 #define BG_MIN_BLOCKS 4
 #endif
@@ -460,6 +463,10 @@ int launch_bg(cudaStream_t s, const void *vis, float *out, const uint8_t *flags,
     }
 #define KSP_BG_CASE(IM, FM)                                                        \
     if (in_mode == IM && flag_mode == FM) {                                        \
+        if (TileGeom<BG_TC>::SMEM_BYTES > 48 * 1024)                               \
+            KSP_CUDA(cudaFuncSetAttribute(bg13_kernel<IM, FM, TRANSPOSED, BG_TC>,  \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                          TileGeom<BG_TC>::SMEM_BYTES));           \
         bg13_kernel<IM, FM, TRANSPOSED, BG_TC>                                     \
             <<<grid, BG_THREADS, TileGeom<BG_TC>::SMEM_BYTES, s>>>(a);             \
         KSP_CHECK_LAUNCH();                                                        \

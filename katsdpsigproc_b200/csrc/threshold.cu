@@ -18,16 +18,15 @@
 //   * mapping: one thread per run of 32 consecutive channels, one block per span of
 //     T * 32 channels of one baseline (spans overlap by the reach of the largest window,
 //     128 channels, so blocks are independent and small: several per SM);
-//   * every thread keeps the running sums p[k] = u[0] + .. + u[k-1] of its run in registers
-//     and publishes them, its 32 flags, and three statistics of the run (maximum of its
+//   * every thread publishes its 32 flags and three statistics of its run (maximum of the
 //     first 8 samples, sum of the positive samples, sum of |u|) in shared memory;
 //   * window size 2^w, thread by thread, cheapest test first:
 //       - sizes 2..8, per group of 8 window starts: no sample of the 16 the group can reach
 //         exceeds thr_w                                  -> none of those windows can fire;
 //       - sizes 16..64: the positive samples within reach add up to less than
 //         thr_w * (2^w - #F within reach)                -> none of the thread's windows can;
-//       - else S~[j] = differences of running sums (own registers + the next one or two runs'
-//         from shared memory); |S~ - D_w| <= E with E = 2.5e-4 * sum|u| within reach
+//       - else S~[j] = differences of running sums p[k] = u[0] + .. + u[k-1] of the own and
+//         the next one or two runs; |S~ - D_w| <= E with E = 2.5e-4 * sum|u| within reach
 //         (3 serial sums of 32 terms, the tree's own 6 roundings, with slack), so
 //         S~[j] <= thr_w * (2^w - #F) - E rules the window out;
 //       - survivors (real interference, or decisions within ~1e-4 of the threshold) are
@@ -44,7 +43,7 @@ using namespace ksp;
 
 constexpr int RUN = 32;
 constexpr int PITCH = 36;            // floats per staged run: 128-bit accesses one run apart are conflict-free
-constexpr int TS_MAX_THREADS = 384;
+constexpr int TS_MAX_THREADS = 256;
 constexpr int TS_MAX_WINDOWS = 7;    // windows up to 64 = two runs of reach
 constexpr unsigned FULL = 0xffffffffu;
 constexpr float FILTER_ERR = 2.5e-4f;
@@ -104,40 +103,36 @@ __device__ __noinline__ uint32_t exact_windows(uint32_t cand, int run_index, int
     return fire;
 }
 
-// Candidate windows of size W (2..64) that start in this thread's run (rare path).
-//   pb0       published running sums p[1..32] of the own run and, PITCH and 2 * PITCH
-//             floats further on, of the next two runs (shared memory)
-//   F, F1, F2 flag words of the three runs;  tw = thr_w;  err = bound on |S~ - D_w|
-template <int W>
-__device__ __noinline__ uint32_t window_candidates(const float *pb0, uint32_t F, uint32_t F1,
-                                                   uint32_t F2, float tw, float err)
+// Running sums p[0..32] of one staged run with its flagged samples zeroed (rare path).
+__device__ __forceinline__ void run_sums(const float *x, uint32_t F, float (&p)[RUN + 1])
 {
-    const float *pb1 = pb0 + PITCH, *pb2 = pb0 + 2 * PITCH;
-    float p[RUN + 1];
     p[0] = 0.0f;
 #pragma unroll
     for (int k = 0; k < RUN / 4; k++) {
-        const float4 q = *reinterpret_cast<const float4 *>(pb0 + 4 * k);
-        p[4 * k + 1] = q.x; p[4 * k + 2] = q.y; p[4 * k + 3] = q.z; p[4 * k + 4] = q.w;
-    }
-    // running sums of the next run that windows of this size can reach: p1[k], k = 1 .. W-1
-    constexpr int NEED1 = (W > RUN) ? RUN : W - 1;
-    float p1[RUN + 1];
-    p1[0] = 0.0f;
+        const float4 q = *reinterpret_cast<const float4 *>(x + 4 * k);
+        const float v[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int k = 0; k < (NEED1 + 3) / 4; k++) {
-        const float4 q = *reinterpret_cast<const float4 *>(pb1 + 4 * k);
-        p1[4 * k + 1] = q.x; p1[4 * k + 2] = q.y; p1[4 * k + 3] = q.z; p1[4 * k + 4] = q.w;
-    }
-    float p2[RUN + 1];
-    p2[0] = 0.0f;
-    if (W > RUN) {
-#pragma unroll
-        for (int k = 0; k < RUN / 4; k++) {
-            const float4 q = *reinterpret_cast<const float4 *>(pb2 + 4 * k);
-            p2[4 * k + 1] = q.x; p2[4 * k + 2] = q.y; p2[4 * k + 3] = q.z; p2[4 * k + 4] = q.w;
+        for (int i = 0; i < 4; i++) {
+            const int j = 4 * k + i;
+            p[j + 1] = p[j] + (((F >> j) & 1u) ? 0.0f : v[i]);
         }
     }
+}
+
+// Candidate windows of size W (2..64) that start in this thread's run (rare path).
+//   x0        the staged samples of the own run; the next two runs follow PITCH and
+//             2 * PITCH floats further on (zeros beyond the span)
+//   F, F1, F2 flag words of the three runs;  tw = thr_w;  err = bound on |S~ - D_w|
+// The running sums are formed exactly as the kernel's rebuild() forms them.
+template <int W>
+__device__ __noinline__ uint32_t window_candidates(const float *x0, uint32_t F, uint32_t F1,
+                                                   uint32_t F2, float tw, float err)
+{
+    float p[RUN + 1], p1[RUN + 1], p2[RUN + 1];
+    run_sums(x0, F, p);
+    run_sums(x0 + PITCH, F1, p1);
+    if (W > RUN) run_sums(x0 + 2 * PITCH, F2, p2);
+    else p2[0] = 0.0f;
     const bool any_flag = (F | F1 | F2) != 0u;
     const float t_full = tw * (float) W;                   // exact: W is a power of two
     const float slack = err + 1.2e-7f * t_full;            // rounding of tw * (W - n) below
@@ -163,7 +158,7 @@ __device__ __noinline__ uint32_t window_candidates(const float *pb0, uint32_t F,
 }
 
 template <bool PACKED>
-__global__ void __launch_bounds__(TS_MAX_THREADS)
+__global__ void __launch_bounds__(TS_MAX_THREADS, 4)
 threshold_sum_kernel(const TsArgs a)
 {
     extern __shared__ __align__(16) float sm[];
@@ -172,9 +167,8 @@ threshold_sum_kernel(const TsArgs a)
     const int span = T * RUN;
     const float neg_inf = -__int_as_float(0x7f800000);
 
-    float *rowbuf = sm;                                        // T * PITCH: the staged samples x
-    float *pbuf = rowbuf + T * PITCH;                          // (T + 2) * PITCH: running sums p[1..32]
-    float4 *stat = reinterpret_cast<float4 *>(pbuf + (T + 2) * PITCH);      // T + 2: run statistics
+    float *rowbuf = sm;                                        // (T + 2) * PITCH: the staged samples x
+    float4 *stat = reinterpret_cast<float4 *>(rowbuf + (T + 2) * PITCH);    // T + 2: run statistics
     uint32_t *Fsm = reinterpret_cast<uint32_t *>(stat + T + 2);             // T + 2
     uint32_t *car1 = Fsm + T + 2;                              // T
     uint32_t *car2 = car1 + T;                                 // T
@@ -191,7 +185,7 @@ threshold_sum_kernel(const TsArgs a)
         Fsm[T + tid] = 0u;
         stat[T + tid] = make_float4(neg_inf, 0.0f, 0.0f, 0.0f);
     }
-    for (int i = tid; i < 2 * PITCH; i += T) pbuf[T * PITCH + i] = 0.0f;
+    for (int i = tid; i < 2 * PITCH; i += T) rowbuf[T * PITCH + i] = 0.0f;   // two runs of zeros past the span
 
     // ---- stage the span: coalesced 128-bit loads -> padded runs (zeros outside the band)
     const bool vec_ok = ((a.dev_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dev_t) & 15) == 0) &&
@@ -235,7 +229,6 @@ threshold_sum_kernel(const TsArgs a)
 
     // ---- my run: window size 1, then running sums of what is left
     const float *my = rowbuf + tid * PITCH;
-    float *myp = pbuf + tid * PITCH;
     const int64_t pos0 = (int64_t) base + (int64_t) tid * RUN;  // row channel of element 0
     const uint32_t in_range = bit_range(-pos0, (int64_t) C - pos0);
 
@@ -257,8 +250,7 @@ threshold_sum_kernel(const TsArgs a)
             F &= in_range;
         }
         sabs = 0.0f;
-        float p[RUN + 1];
-        p[0] = 0.0f;
+        float total = 0.0f;
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             float m = neg_inf;
@@ -268,15 +260,11 @@ threshold_sum_kernel(const TsArgs a)
                 const float u = ((F >> j) & 1u) ? 0.0f : x[j];
                 m = fmaxf(m, u);
                 sabs += fabsf(u);
-                p[j + 1] = p[j] + u;
+                total += u;
             }
             m8[g] = m;
         }
-        ppos = 0.5f * (p[RUN] + sabs) * 1.00002f;              // >= sum of max(u, 0), with slack
-#pragma unroll
-        for (int i = 0; i < RUN / 4; i++)
-            *reinterpret_cast<float4 *>(myp + 4 * i) =
-                make_float4(p[4 * i + 1], p[4 * i + 2], p[4 * i + 3], p[4 * i + 4]);
+        ppos = 0.5f * (total + sabs) * 1.00002f;               // >= sum of max(u, 0), with slack
         Fsm[tid] = F;
         stat[tid] = make_float4(m8[0], ppos, sabs, 0.0f);
     };
@@ -325,12 +313,12 @@ threshold_sum_kernel(const TsArgs a)
                 const uint32_t G2 = two ? F2 : 0u;
                 uint32_t cand;
                 switch (w) {
-                case 1: cand = window_candidates<2>(myp, F, F1, G2, tw, err); break;
-                case 2: cand = window_candidates<4>(myp, F, F1, G2, tw, err); break;
-                case 3: cand = window_candidates<8>(myp, F, F1, G2, tw, err); break;
-                case 4: cand = window_candidates<16>(myp, F, F1, G2, tw, err); break;
-                case 5: cand = window_candidates<32>(myp, F, F1, G2, tw, err); break;
-                default: cand = window_candidates<64>(myp, F, F1, G2, tw, err); break;
+                case 1: cand = window_candidates<2>(my, F, F1, G2, tw, err); break;
+                case 2: cand = window_candidates<4>(my, F, F1, G2, tw, err); break;
+                case 3: cand = window_candidates<8>(my, F, F1, G2, tw, err); break;
+                case 4: cand = window_candidates<16>(my, F, F1, G2, tw, err); break;
+                case 5: cand = window_candidates<32>(my, F, F1, G2, tw, err); break;
+                default: cand = window_candidates<64>(my, F, F1, G2, tw, err); break;
                 }
                 cand &= hot;
                 if (cand != 0u) fire = exact_windows(cand, tid, w, tw, rowbuf, Fsm, span);
@@ -495,8 +483,7 @@ expand_flags_kernel(const uint32_t *__restrict__ bits_t, uint8_t *__restrict__ f
 
 size_t ts_smem_bytes(int threads)
 {
-    return sizeof(float) * ((size_t) threads * PITCH + ((size_t) threads + 2) * PITCH +
-                            7 * ((size_t) threads + 2) + 16);
+    return sizeof(float) * (((size_t) threads + 2) * PITCH + 7 * ((size_t) threads + 2) + 16);
 }
 
 int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise, uint8_t *flags_t,
