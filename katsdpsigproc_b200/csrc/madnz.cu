@@ -13,6 +13,7 @@
 // (hist[digit][lane]: conflict-free).
 #include "common.cuh"
 #include "select.cuh"
+#include <math.h>
 
 namespace {
 
@@ -509,6 +510,233 @@ percentile5_kernel(const void *__restrict__ src, float *__restrict__ dest, int64
     }
 }
 
+// ------------------------------------------------------------------ streaming Percentile5
+// Same idea as madnz_stream_kernel, for three ranks at once: brackets around the 25 %, 50 % and
+// 75 % ranks from 1024 samples of the row, ONE pass over the row (amplitude computed once per
+// element) that tracks min / max, counts the keys below each bracket and keeps the keys inside
+// any bracket (~36 %) in thread-private lists, then three small selections inside the lists.
+// A rank whose bracket misses it, or a list that overflows, falls back to the radix select
+// over global memory for that rank.  Replaces reference percentile.mako:115-140.
+constexpr int P5_THREADS = 256;
+constexpr int P5_MIN_SLOTS = 24;
+
+struct P5Brackets {
+    uint32_t lo[3], width[3];     // bracket k = keys in [lo, lo + width)
+};
+
+template <int MODE>   // 0: float32 amplitudes, 1: complex64 numpy rule, 2: complex64 hypot rule
+__device__ __forceinline__ uint32_t p5_key(const void *src, int64_t index)
+{
+    float v;
+    if (MODE == 0) {
+        v = fabsf(reinterpret_cast<const float *>(src)[index]);
+    } else {
+        const float2 z = reinterpret_cast<const float2 *>(src)[index];
+        v = abs_c64<MODE == 1 ? KSP_ABS_NUMPY : KSP_ABS_HYPOT>(z.x, z.y);
+    }
+    return float_to_key(v);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(P5_THREADS)
+percentile5_stream_kernel(const void *__restrict__ src, float *__restrict__ dest, int64_t src_stride,
+                          int64_t dest_stride, int64_t first_col, int n, int slots)
+{
+    extern __shared__ __align__(16) uint32_t p5_smem[];
+    uint32_t *lists = p5_smem;                               // slots * P5_THREADS (>= SELECT_HIST_WORDS)
+    uint32_t *hist = lists + (size_t) slots * P5_THREADS;    // MS_BINS
+    uint32_t *misc = hist + MS_BINS;                         // 320 words
+    // misc: 0..2 below[k], 3 overflow, 4 kmin, 5 kmax, 6 bin, 7 before bin, 8 in bin, 9 small count,
+    //       10..15 bounds (lo0 hi0 lo1 hi1 lo2 hi2), 16..63 scan / fallback scratch,
+    //       64..255 group picks (6 x 32), 256..287 small list
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NWARPS = P5_THREADS / 32;
+    const int64_t off = (int64_t) blockIdx.x * src_stride + first_col;
+    const uint32_t nn = (uint32_t) n;
+    const uint32_t ranks[3] = {(nn - 1) / 4, ((nn - 1) * 3) / 4, (nn - 1) / 2};   // 25 %, 75 %, 50 %
+
+    if (tid < 16) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
+
+    // ---- 1. brackets
+    {
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const int i = tid * 4 + g;
+            const int pos = (int) (((int64_t) i * n) >> 10);
+            const uint32_t key = p5_key<MODE>(src, off + min(pos, n - 1));
+            const uint32_t sorted = sort32(key, lane);
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                // group quantiles 6 % either side of the wanted rank (of the 32 samples of a group)
+                const float q = (float) ranks[k] / (float) max(nn - 1u, 1u);
+                const int i_lo = (int) floorf((q - 0.06f) * 32.0f);
+                const int i_hi = (int) ceilf((q + 0.06f) * 32.0f);
+                const uint32_t lo_g = __shfl_sync(0xffffffffu, sorted, max(i_lo, 0));
+                const uint32_t hi_g = __shfl_sync(0xffffffffu, sorted, min(i_hi, 31));
+                if (lane == 0) {
+                    misc[64 + (2 * k) * 32 + warp * 4 + g] = (i_lo < 0) ? 0u : lo_g;
+                    misc[64 + (2 * k + 1) * 32 + warp * 4 + g] = (i_hi > 31) ? 0xffffffffu : hi_g;
+                }
+            }
+        }
+        __syncthreads();
+        if (warp < 6) {
+            const uint32_t v = misc[64 + 32 * warp + lane];
+            const uint32_t s = sort32(v, lane);
+            // lower bounds take the lower median of the groups, upper bounds the upper one
+            const uint32_t pick = __shfl_sync(0xffffffffu, s, (warp & 1) ? 16 : 15);
+            if (lane == 0) misc[10 + warp] = pick;
+        }
+        __syncthreads();
+    }
+    P5Brackets br;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        br.lo[k] = misc[10 + 2 * k];
+        const uint32_t hi = max(misc[11 + 2 * k], br.lo[k]);
+        br.width[k] = (hi == 0xffffffffu && br.lo[k] == 0u) ? 0xffffffffu : hi - br.lo[k] + 1u;
+    }
+
+    // ---- 2. one pass over the row
+    uint32_t n_mine = 0;
+    {
+        uint32_t below0 = 0, below1 = 0, below2 = 0, kmin = 0xffffffffu, kmax = 0u;
+        uint32_t *slot = lists + tid;
+        for (int i = tid; i < n; i += P5_THREADS) {
+            const uint32_t key = p5_key<MODE>(src, off + i);
+            kmin = min(kmin, key);
+            kmax = max(kmax, key);
+            below0 += (key < br.lo[0]) ? 1u : 0u;
+            below1 += (key < br.lo[1]) ? 1u : 0u;
+            below2 += (key < br.lo[2]) ? 1u : 0u;
+            const bool in = (key - br.lo[0] < br.width[0]) || (key - br.lo[1] < br.width[1]) ||
+                            (key - br.lo[2] < br.width[2]);
+            if (in) {
+                if (n_mine < (uint32_t) slots) *slot = key;
+                slot += P5_THREADS;
+                n_mine++;
+            }
+        }
+        below0 = __reduce_add_sync(0xffffffffu, below0);
+        below1 = __reduce_add_sync(0xffffffffu, below1);
+        below2 = __reduce_add_sync(0xffffffffu, below2);
+        kmin = __reduce_min_sync(0xffffffffu, kmin);
+        kmax = __reduce_max_sync(0xffffffffu, kmax);
+        const bool over = __any_sync(0xffffffffu, n_mine > (uint32_t) slots);
+        if (lane == 0) {
+            atomicAdd(&misc[0], below0);
+            atomicAdd(&misc[1], below1);
+            atomicAdd(&misc[2], below2);
+            atomicMin(&misc[4], kmin);
+            atomicMax(&misc[5], kmax);
+            if (over) misc[3] = 1u;
+        }
+    }
+    __syncthreads();
+    const bool overflow = misc[3] != 0u;
+    const uint32_t *mine = lists + tid;
+
+    // ---- 3. the three selections
+    uint32_t found[3];
+    bool redo[3];
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        const uint32_t lo = br.lo[k], width = br.width[k];
+        const uint32_t r_rel = ranks[k] - misc[k];               // wraps if the rank is below the bracket
+        redo[k] = overflow;
+        found[k] = 0;
+        if (overflow) continue;                                  // block-uniform
+        for (int i = tid; i < MS_BINS; i += P5_THREADS) hist[i] = 0u;
+        if (tid == 0) misc[9] = 0u;
+        __syncthreads();
+        const int shift = (width <= (uint32_t) MS_BINS) ? 0 : (32 - __clz(width - 1u)) - 11;
+        for (uint32_t j = 0; j < n_mine; j++) {
+            const uint32_t d = mine[j * P5_THREADS] - lo;
+            if (d < width) atomicAdd(&hist[d >> shift], 1u);
+        }
+        __syncthreads();
+        {
+            constexpr int BPT = MS_BINS / P5_THREADS;
+            uint32_t h[BPT], own = 0;
+#pragma unroll
+            for (int b = 0; b < BPT; b++) {
+                h[b] = hist[tid * BPT + b];
+                own += h[b];
+            }
+            uint32_t incl = own;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += o;
+            }
+            if (lane == 31) misc[16 + warp] = incl;
+            __syncthreads();
+            const uint32_t w = (lane < NWARPS) ? misc[16 + lane] : 0u;
+            const uint32_t total = __reduce_add_sync(0xffffffffu, w);
+            uint32_t cum = __reduce_add_sync(0xffffffffu, lane < warp ? w : 0u) + incl - own;
+            if (tid == 0) misc[8] = 0xffffffffu;                 // "not found" unless a thread finds it
+            __syncthreads();
+            if (r_rel < total && r_rel >= cum && r_rel < cum + own) {
+#pragma unroll
+                for (int b = 0; b < BPT; b++) {
+                    if (r_rel >= cum && r_rel < cum + h[b]) {
+                        misc[6] = (uint32_t) (tid * BPT + b);
+                        misc[7] = cum;
+                        misc[8] = h[b];
+                    }
+                    cum += h[b];
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t bin = misc[6], in_bin = misc[8];
+        if (in_bin == 0xffffffffu || in_bin > (uint32_t) MS_SMALL_CAP) {
+            redo[k] = true;                                      // bracket missed or crowded bin
+            continue;
+        }
+        const uint32_t r_bin = r_rel - misc[7];
+        if (shift == 0) {
+            found[k] = lo + bin;
+            continue;
+        }
+        for (uint32_t j = 0; j < n_mine; j++) {
+            const uint32_t key = mine[j * P5_THREADS];
+            const uint32_t d = key - lo;
+            if (d < width && (d >> shift) == bin) misc[256 + atomicAdd(&misc[9], 1u)] = key;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t sorted = sort32(lane < (int) in_bin ? misc[256 + lane] : 0xffffffffu, lane);
+            const uint32_t pick = __shfl_sync(0xffffffffu, sorted, (int) r_bin);
+            if (lane == 0) misc[16] = pick;
+        }
+        __syncthreads();
+        found[k] = misc[16];
+        __syncthreads();
+    }
+    // ---- fallbacks: radix select over the row in global memory
+#pragma unroll 1
+    for (int k = 0; k < 3; k++) {
+        if (!redo[k]) continue;                                  // block-uniform
+        __syncthreads();
+        SelectScratch sc;
+        sc.hist = lists;
+        sc.misc = misc + 16;
+        auto key_at = [src, off](int i) { return p5_key<MODE>(src, off + i); };
+        found[k] = block_radix_select<P5_THREADS>(key_at, n, ranks[k], sc);
+    }
+    if (tid == 0) {
+        const int64_t r = blockIdx.x;
+        dest[0 * dest_stride + r] = key_to_float(misc[4]);
+        dest[1 * dest_stride + r] = key_to_float(misc[5]);
+        dest[2 * dest_stride + r] = key_to_float(found[0]);
+        dest[3 * dest_stride + r] = key_to_float(found[1]);
+        dest[4 * dest_stride + r] = key_to_float(found[2]);
+    }
+}
+
+int baselines_limit_ok(int64_t rows) { return rows > 0x7fffffff ? 1 : 0; }
+
 size_t select_smem_bytes(int64_t n, bool in_smem)
 {
     return (size_t) (SELECT_HIST_WORDS + 64 + (in_smem ? ((n + 3) & ~(int64_t) 3) : 0)) * 4;
@@ -554,19 +782,35 @@ extern "C" int ksp_percentile5(void *stream, const void *src, float *dest, int64
     if (n_cols > (int64_t) 1 << 30) return KSP_ETOOLARGE;
     if (abs_mode != KSP_ABS_NUMPY && abs_mode != KSP_ABS_HYPOT) return KSP_EINVAL;
     cudaStream_t s = (cudaStream_t) stream;
-    const bool in_smem = n_cols <= SMEM_KEY_CAP;
-    const size_t smem = select_smem_bytes(n_cols, in_smem);
-    if (in_smem) {
-        KSP_CUDA(cudaFuncSetAttribute(percentile5_kernel<true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        percentile5_kernel<true><<<(unsigned) rows, SEL_THREADS, smem, s>>>(
-            src, dest, src_stride, dest_stride, first_col, (int) n_cols, is_amplitude, abs_mode);
-    } else {
-        KSP_CUDA(cudaFuncSetAttribute(percentile5_kernel<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        percentile5_kernel<false><<<(unsigned) rows, SEL_THREADS, smem, s>>>(
-            src, dest, src_stride, dest_stride, first_col, (int) n_cols, is_amplitude, abs_mode);
+    if (baselines_limit_ok(rows) != 0) return KSP_ETOOLARGE;
+    // list slots per thread: the three brackets keep ~36 % of a thread's n / 256 keys
+    const int64_t per_thread = ksp_divup(n_cols, P5_THREADS);
+    int64_t slots = (per_thread * 36 + 99) / 100 + 5 * (int64_t) ceil(sqrt(0.23 * (double) per_thread)) + 4;
+    if (slots < P5_MIN_SLOTS) slots = P5_MIN_SLOTS;
+    if (slots * P5_THREADS < SELECT_HIST_WORDS) slots = SELECT_HIST_WORDS / P5_THREADS;
+    const size_t smem = ((size_t) slots * P5_THREADS + MS_BINS + 320) * sizeof(uint32_t);
+    if (smem <= 200 * 1024) {
+        const int mode = is_amplitude ? 0 : (abs_mode == KSP_ABS_NUMPY ? 1 : 2);
+#define KSP_P5_CASE(M)                                                                         \
+        if (mode == M) {                                                                       \
+            KSP_CUDA(cudaFuncSetAttribute(percentile5_stream_kernel<M>,                        \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+            percentile5_stream_kernel<M><<<(unsigned) rows, P5_THREADS, smem, s>>>(            \
+                src, dest, src_stride, dest_stride, first_col, (int) n_cols, (int) slots);     \
+        }
+        KSP_P5_CASE(0)
+        KSP_P5_CASE(1)
+        KSP_P5_CASE(2)
+#undef KSP_P5_CASE
+        KSP_CHECK_LAUNCH();
+        return 0;
     }
+    // very long rows: block-wide radix select re-reading global memory
+    const size_t smem_old = select_smem_bytes(n_cols, false);
+    KSP_CUDA(cudaFuncSetAttribute(percentile5_kernel<false>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem_old));
+    percentile5_kernel<false><<<(unsigned) rows, SEL_THREADS, smem_old, s>>>(
+        src, dest, src_stride, dest_stride, first_col, (int) n_cols, is_amplitude, abs_mode);
     KSP_CHECK_LAUNCH();
     return 0;
 }
