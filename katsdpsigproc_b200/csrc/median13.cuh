@@ -42,13 +42,39 @@ KSP_HD void mid4_of_10(float v0, float v1, float v2, float v3, float v4, float v
     m0 = v3; m1 = v4; m2 = v5; m3 = v6;
 }
 
-// Median of the 7 values {m0<=m1<=m2<=m3} U {b0<=b1<=b2}: the 4th smallest.
-KSP_HD float median7_sorted43(float m0, float m1, float m2, float m3, float b0, float b1, float b2)
+// 3-input min / max: one FMNMX3 on sm_100a (the host build composes two).
+KSP_HD float ksp_min3(float a, float b, float c)
 {
-    float t0 = fmaxf(m0, b2);
-    float t1 = fmaxf(m1, b1);
-    float t2 = fmaxf(m2, b0);
-    return fminf(fminf(t0, t1), fminf(t2, m3));
+#ifdef __CUDA_ARCH__
+    float d;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+#else
+    return fminf(fminf(a, b), c);
+#endif
+}
+KSP_HD float ksp_max3(float a, float b, float c)
+{
+#ifdef __CUDA_ARCH__
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+#else
+    return fmaxf(fmaxf(a, b), c);
+#endif
+}
+
+// Median of the 7 values {m0<=m1<=m2<=m3} U {x, p0<=p1}: the 4th smallest.
+// With b0<=b1<=b2 the sorted extras (b0 = min(x,p0), b1 = clamp(x,p0,p1), b2 = max(x,p1)) it is
+//   min( max(m0,b2), max(m1,b1), max(m2,b0), m3 )
+// and the extras never need to be formed: 7 operations with 3-input min/max.
+KSP_HD float median7_core4_extras3(float m0, float m1, float m2, float m3, float x, float p0,
+                                   float p1)
+{
+    const float t0 = ksp_max3(m0, x, p1);                  // max(m0, b2)
+    const float t1 = ksp_max3(m1, p0, fminf(x, p1));       // max(m1, b1)
+    const float t2 = fmaxf(m2, fminf(x, p0));              // max(m2, b0)
+    return fminf(ksp_min3(t0, t1, t2), m3);
 }
 
 // Four medians of 13 from 16 consecutive samples: out[j] = median(e[j .. j+12]).
@@ -59,32 +85,12 @@ KSP_HD void median13x4(const float (&e)[16], int rot, float &o0, float &o1, floa
     float m0, m1, m2, m3;
     mid4_of_10(E(3), E(4), E(5), E(6), E(7), E(8), E(9), E(10), E(11), E(12), m0, m1, m2, m3);
     // left extras {e0,e1,e2} / {e1,e2}; right extras {e13,e14} / {e13,e14,e15}
-    float p0 = fminf(E(1), E(2)), p1 = fmaxf(E(1), E(2));
-    float q0 = fminf(E(13), E(14)), q1 = fmaxf(E(13), E(14));
-    {   // output 0: extras e0, p0, p1
-        float x = E(0);
-        float b0 = fminf(x, p0), t = fmaxf(x, p0);
-        float b1 = fminf(t, p1), b2 = fmaxf(t, p1);
-        o0 = median7_sorted43(m0, m1, m2, m3, b0, b1, b2);
-    }
-    {   // output 1: extras p0, p1, e13
-        float x = E(13);
-        float b0 = fminf(x, p0), t = fmaxf(x, p0);
-        float b1 = fminf(t, p1), b2 = fmaxf(t, p1);
-        o1 = median7_sorted43(m0, m1, m2, m3, b0, b1, b2);
-    }
-    {   // output 2: extras e2, q0, q1
-        float x = E(2);
-        float b0 = fminf(x, q0), t = fmaxf(x, q0);
-        float b1 = fminf(t, q1), b2 = fmaxf(t, q1);
-        o2 = median7_sorted43(m0, m1, m2, m3, b0, b1, b2);
-    }
-    {   // output 3: extras q0, q1, e15
-        float x = E(15);
-        float b0 = fminf(x, q0), t = fmaxf(x, q0);
-        float b1 = fminf(t, q1), b2 = fmaxf(t, q1);
-        o3 = median7_sorted43(m0, m1, m2, m3, b0, b1, b2);
-    }
+    const float p0 = fminf(E(1), E(2)), p1 = fmaxf(E(1), E(2));
+    const float q0 = fminf(E(13), E(14)), q1 = fmaxf(E(13), E(14));
+    o0 = median7_core4_extras3(m0, m1, m2, m3, E(0), p0, p1);    // extras e0, e1, e2
+    o1 = median7_core4_extras3(m0, m1, m2, m3, E(13), p0, p1);   // extras e1, e2, e13
+    o2 = median7_core4_extras3(m0, m1, m2, m3, E(2), q0, q1);    // extras e2, e13, e14
+    o3 = median7_core4_extras3(m0, m1, m2, m3, E(15), q0, q1);   // extras e13, e14, e15
 #undef E
 }
 
