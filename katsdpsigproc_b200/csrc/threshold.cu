@@ -277,37 +277,56 @@ threshold_sum_kernel(const TsArgs a)
     float4 st1 = stat[tid + 1], st2 = stat[tid + 2];
     uint32_t F1 = Fsm[tid + 1], F2 = Fsm[tid + 2];
 
+    // window starts of size 2^w in my run that the cheap tests cannot rule out
+    auto hot_starts = [&](int w, float tw) -> uint32_t {
+        const int win = 1 << w;
+        const bool two = win > RUN;                            // reach covers two more runs
+        // windows that start in my run and lie inside the band
+        const uint32_t valid = interior ? FULL
+                                        : bit_range(-pos0, (int64_t) C - (int64_t) win - pos0 + 1);
+        uint32_t hot = FULL;
+        if (tw >= 0.0f) {
+            if (win <= 8) {
+                // a window of unflagged samples that are all <= thr_w cannot fire
+                const float lim = __fmul_rd(tw, 0.99999905f);
+                hot = 0u;
+                hot |= !(fmaxf(m8[0], m8[1]) <= lim) ? 0x000000ffu : 0u;
+                hot |= !(fmaxf(m8[1], m8[2]) <= lim) ? 0x0000ff00u : 0u;
+                hot |= !(fmaxf(m8[2], m8[3]) <= lim) ? 0x00ff0000u : 0u;
+                hot |= !(fmaxf(m8[3], st1.x) <= lim) ? 0xff000000u : 0u;
+            } else {
+                // no window sum exceeds the sum of the positive samples within reach
+                const float bound = ppos + st1.y + (two ? st2.y : 0.0f);
+                const int nf = __popc(F) + __popc(F1) + (two ? __popc(F2) : 0);
+                const float t_min = tw * (float) max(win - nf, 0);
+                if (bound <= __fmul_rd(t_min, 0.99999f)) hot = 0u;
+            }
+        }
+        return hot & valid;
+    };
+
+    // Almost always no thread of the block has anything left to look at: one vote then
+    // replaces the whole window-size loop (and its barrier per size).
+    {
+        bool any = false;
+        for (int w = 1; w < a.n_windows; w++) {
+            if ((1 << w) > C) break;
+            const float tw = thr[w];
+            if (tw != tw) continue;
+            any |= hot_starts(w, tw) != 0u;
+        }
+        if (!__syncthreads_or(any)) goto write_out;
+    }
+
     for (int w = 1; w < a.n_windows; w++) {
         const int win = 1 << w;
         if (win > C) break;
         const float tw = thr[w];
         if (tw != tw) continue;                                // NaN threshold: nothing can fire
-        // windows that start in my run and lie inside the band
-        const uint32_t valid = interior ? FULL
-                                        : bit_range(-pos0, (int64_t) C - (int64_t) win - pos0 + 1);
         uint32_t fire = 0;
-        if (valid != 0u) {
-            const bool two = win > RUN;                        // reach covers two more runs
-            // groups of 8 window starts that cannot be ruled out wholesale
-            uint32_t hot = FULL;
-            if (tw >= 0.0f) {
-                if (win <= 8) {
-                    // a window of unflagged samples that are all <= thr_w cannot fire
-                    const float lim = __fmul_rd(tw, 0.99999905f);
-                    hot = 0u;
-                    hot |= !(fmaxf(m8[0], m8[1]) <= lim) ? 0x000000ffu : 0u;
-                    hot |= !(fmaxf(m8[1], m8[2]) <= lim) ? 0x0000ff00u : 0u;
-                    hot |= !(fmaxf(m8[2], m8[3]) <= lim) ? 0x00ff0000u : 0u;
-                    hot |= !(fmaxf(m8[3], st1.x) <= lim) ? 0xff000000u : 0u;
-                } else {
-                    // no window sum exceeds the sum of the positive samples within reach
-                    const float bound = ppos + st1.y + (two ? st2.y : 0.0f);
-                    const int nf = __popc(F) + __popc(F1) + (two ? __popc(F2) : 0);
-                    const float t_min = tw * (float) max(win - nf, 0);
-                    if (bound <= __fmul_rd(t_min, 0.99999f)) hot = 0u;
-                }
-            }
-            hot &= valid;
+        {
+            const bool two = win > RUN;
+            uint32_t hot = hot_starts(w, tw);
             if (hot != 0u) {
                 const float err = FILTER_ERR * ((sabs + st1.z) + (two ? st2.z : 0.0f));
                 const uint32_t G2 = two ? F2 : 0u;
@@ -354,6 +373,7 @@ threshold_sum_kernel(const TsArgs a)
         }
     }
 
+write_out:
     // ---- write my 32 flags if my run belongs to this block's output range
     const int64_t out_lo = (int64_t) blockIdx.y * a.chunk_valid;
     const int64_t out_hi = min((int64_t) C, out_lo + (int64_t) a.chunk_valid);
