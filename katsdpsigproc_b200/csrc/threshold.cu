@@ -157,12 +157,14 @@ __device__ __noinline__ uint32_t window_candidates(const float *x0, uint32_t F, 
     return cand;
 }
 
-template <bool PACKED>
-__global__ void __launch_bounds__(TS_MAX_THREADS, 4)
+// TFIX: block size known at compile time (0 = use blockDim.x); lets the staging loop use
+// immediate offsets.
+template <bool PACKED, int TFIX>
+__global__ void __launch_bounds__(TFIX ? TFIX : TS_MAX_THREADS, TFIX ? 6 : 4)
 threshold_sum_kernel(const TsArgs a)
 {
     extern __shared__ __align__(16) float sm[];
-    const int T = blockDim.x;
+    const int T = TFIX ? TFIX : (int) blockDim.x;
     const int tid = threadIdx.x;
     const int span = T * RUN;
     const float neg_inf = -__int_as_float(0x7f800000);
@@ -244,10 +246,19 @@ threshold_sum_kernel(const TsArgs a)
             x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
         }
         if (first) {
+            // window size 1: flag and zero in one go (samples outside the band are zeros and
+            // stay zeros whether or not their bit survives the mask)
             const float t0 = thr[0];
 #pragma unroll
-            for (int j = 0; j < RUN; j++) F |= (x[j] > t0) ? (1u << j) : 0u;
+            for (int j = 0; j < RUN; j++) {
+                const bool f = x[j] > t0;
+                F |= f ? (1u << j) : 0u;
+                x[j] = f ? 0.0f : x[j];
+            }
             F &= in_range;
+        } else {
+#pragma unroll
+            for (int j = 0; j < RUN; j++) x[j] = ((F >> j) & 1u) ? 0.0f : x[j];
         }
         sabs = 0.0f;
         float total = 0.0f;
@@ -257,7 +268,7 @@ threshold_sum_kernel(const TsArgs a)
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int j = 8 * g + k;
-                const float u = ((F >> j) & 1u) ? 0.0f : x[j];
+                const float u = x[j];
                 m = fmaxf(m, u);
                 sabs += fabsf(u);
                 total += u;
@@ -556,16 +567,13 @@ int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise,
     if (n_chunks > 65535) return KSP_ETOOLARGE;
     dim3 grid((unsigned) baselines, (unsigned) n_chunks);
     const size_t smem = ts_smem_bytes(threads);
+    // (the largest block needs less than the default 48 KB of dynamic shared memory)
     if (bits_t) {
-        KSP_CUDA(cudaFuncSetAttribute(threshold_sum_kernel<true>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int) ts_smem_bytes(TS_MAX_THREADS)));
-        threshold_sum_kernel<true><<<grid, threads, smem, s>>>(a);
+        if (threads == 128) threshold_sum_kernel<true, 128><<<grid, threads, smem, s>>>(a);
+        else threshold_sum_kernel<true, 0><<<grid, threads, smem, s>>>(a);
     } else {
-        KSP_CUDA(cudaFuncSetAttribute(threshold_sum_kernel<false>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int) ts_smem_bytes(TS_MAX_THREADS)));
-        threshold_sum_kernel<false><<<grid, threads, smem, s>>>(a);
+        if (threads == 128) threshold_sum_kernel<false, 128><<<grid, threads, smem, s>>>(a);
+        else threshold_sum_kernel<false, 0><<<grid, threads, smem, s>>>(a);
     }
     KSP_CHECK_LAUNCH();
     return 0;
