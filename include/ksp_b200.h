@@ -123,8 +123,8 @@ int ksp_background_median_filter_t(void *stream, const void *vis, float *dev_t,
                                    int width, int is_amplitude, int flag_mode, int abs_mode);
 
 /* noise[b] = float32(1.4826 * median{|dev| : |dev| > 0}) per baseline; NaN if no
- * such sample.  Baseline-major input.  Replaces rfi/madnz_t.mako:72-87 /
- * rfi/device.py:594-607. */
+ * such sample.  Baseline-major input, rows of any length (streamed once).
+ * Replaces rfi/madnz_t.mako:72-87 / rfi/device.py:594-607. */
 int ksp_madnz_t(void *stream, const float *dev_t, float *noise, int64_t channels,
                 int64_t baselines, int64_t stride);
 
@@ -167,9 +167,10 @@ int ksp_maskedsum(void *stream, const void *src, const float *mask, void *dest, 
 
 /* ------------------------------------------------------------------------
  * Fused flagger: the standard median + MAD + SumThreshold combination of
- * rfi/device.py:1111-1166 in three launches per baseline chunk, with the
- * intermediates (baseline-major deviations, bit-packed flags) kept in an
- * L2-resident scratch instead of round-tripping through HBM.
+ * rfi/device.py:1111-1166 in four launches per baseline chunk (background
+ * written baseline-major, noise, thresholds with bit-packed flags, expansion to
+ * channel-major bytes).  Several chunks are in flight on internal streams that
+ * fork from / join into `stream`; the scratch holds every chunk in flight.
  * ---------------------------------------------------------------------- */
 typedef struct ksp_flagger_params {
     int64_t channels, baselines;
@@ -184,7 +185,7 @@ typedef struct ksp_flagger_params {
     int flag_value;
     double n_sigma;
     double scales[KSP_MAX_WINDOWS];
-    int64_t chunk_baselines;     /* 0 = choose from the device's L2 size */
+    int64_t chunk_baselines;     /* 0 = one chunk per lane (KSP_LANES, default 4; KSP_CHUNK overrides) */
 } ksp_flagger_params;
 
 size_t ksp_flagger_scratch_bytes(const ksp_flagger_params *p);

@@ -1,16 +1,16 @@
 // Fused flagger: the standard median + MAD + SumThreshold combination of
 // reference rfi/device.py:1111-1166 (5 launches, 31 B/vis of HBM traffic) as
-// 4 launches per CHUNK of baselines whose intermediates stay in L2:
+// 4 launches per CHUNK of baselines:
 //
-//   vis[:, chunk] --bg13_t--> dev_t (chunk x C float32, scratch)
-//                 --madnz_t--> noise[chunk]
-//                 --threshold_sum (packed)--> bits_t (chunk x C/32 words, scratch)
-//                 --expand_flags--> flags[:, chunk]
+//   vis[:, chunk] --bg13_kernel--> dev_t (chunk x C float32, scratch)
+//                 --madnz_stream_kernel--> noise[chunk]
+//                 --threshold_sum_kernel (packed)--> bits_t (chunk x C/32 words, scratch)
+//                 --expand_flags_kernel--> flags[:, chunk]
 //
-// Compulsory HBM traffic is then the 8 B/vis read of vis and the 1 B/vis write
-// of flags; the 4 + 4 B/vis of dev_t and the 1/8 + 1/8 B/vis of bits_t are
-// written and re-read while still resident in the 126 MB L2 (the scratch is
-// reused chunk after chunk, so its lines are overwritten before eviction).
+// The float transpose of the reference is folded into the background kernel's
+// store, the uchar transpose into the bit -> byte expansion.  Consecutive chunks
+// run on separate internal streams ("lanes", each with its own scratch) that fork
+// from and join into the caller's stream, so kernel tails overlap.
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -31,7 +31,7 @@ struct Layout {
     int lanes;            // chunks in flight (1 = everything on the caller's stream)
 };
 
-constexpr int MAX_LANES = 4;
+constexpr int MAX_LANES = 8;
 
 // Internal streams and events for running several chunks at a time (per device, created on
 // first use, never destroyed: they live as long as the process).
@@ -65,14 +65,13 @@ Layout make_layout(const ksp_flagger_params *p)
     Layout l;
     l.dev_stride = ksp_divup(p->channels, 32) * 32;
     l.words_stride = ksp_divup(ksp_divup(p->channels, 32), 4) * 4;
-    const int64_t row_bytes = (l.dev_stride + l.words_stride) * 4;
     // Chunks in flight ("lanes", KSP_LANES, default 4): consecutive chunks run on separate
     // internal streams so that the tail of one kernel overlaps the next chunk's kernels.
     // Measured on B200 (profiles/): the stages are issue-bound rather than HBM-bound and launches
     // cost ~9 us each, so few large chunks beat many L2-sized ones; the default is one chunk per
     // lane, at most 32 baselines per SM each (KSP_CHUNK / chunk_baselines override).
     const char *e = getenv("KSP_LANES");
-    int lanes = e ? atoi(e) : MAX_LANES;
+    int lanes = e ? atoi(e) : 4;
     if (lanes < 1) lanes = 1;
     if (lanes > MAX_LANES) lanes = MAX_LANES;
     int64_t chunk = p->chunk_baselines;
@@ -84,7 +83,6 @@ Layout make_layout(const ksp_flagger_params *p)
             const int64_t cap = 32 * (int64_t) ksp_sm_count();
             if (chunk > cap) chunk = cap;
         }
-        (void) row_bytes;
     }
     chunk = (chunk / 32) * 32;
     if (chunk < 32) chunk = 32;

@@ -4,12 +4,13 @@
 // madnz    : replaces reference rfi/madnz.mako:105-123 (channel-major input).
 // percentile5 : replaces reference percentile.mako:115-140.
 //
-// All three are exact selections.  madnz_t / percentile5 give
-// one thread block per row: the row is read once from global memory, turned into
-// order-preserving 32-bit keys in shared memory (rows up to 49 152 elements; longer
-// rows are re-read from L2), and block_radix_select (select.cuh) finds the ranks.
-// madnz (channel-major) gives one block per 32 baselines, lane == baseline, and
-// makes its 4 radix passes over global memory with per-baseline histograms
+// All three are exact selections.  madnz_t and percentile5 stream each
+// row ONCE through a 256-thread block: a bracket around the wanted rank(s) from 1024 samples,
+// one pass that counts the keys below the bracket and keeps the few inside it, and a small
+// selection among those (madnz_stream_kernel, percentile5_stream_kernel below).  The
+// block-wide radix select of select.cuh is the fallback for rows whose bracket misses and for
+// very long Percentile5 rows.  madnz (channel-major) gives one block per 32 baselines,
+// lane == baseline, and makes 4 radix passes over global memory with per-baseline histograms
 // (hist[digit][lane]: conflict-free).
 #include "common.cuh"
 #include "select.cuh"
@@ -332,7 +333,7 @@ madnz_cm_kernel(const float *__restrict__ dev, float *__restrict__ noise, int ch
 {
     __shared__ uint32_t hist[256 * 32];   // hist[digit][lane]
     __shared__ uint32_t part[32][33];     // per-warp partials
-    __shared__ uint32_t s_prefix[32], s_rank[32], s_nvalid[32], s_next[32], s_cle[32];
+    __shared__ uint32_t s_prefix[32], s_rank[32], s_nvalid[32], s_next[32];
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b_raw = blockIdx.x * 32 + lane;
@@ -422,7 +423,6 @@ madnz_cm_kernel(const float *__restrict__ dev, float *__restrict__ noise, int ch
     if (warp == 0) {
         uint32_t t = 0;
         for (int w = 0; w < 32; w++) t += part[w][lane];
-        s_cle[lane] = t;
         if (ok) {
             uint32_t n = s_nvalid[lane];
             float out = __int_as_float(0x7fc00000);
