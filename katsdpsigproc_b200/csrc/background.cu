@@ -93,7 +93,6 @@ constexpr int HALO_R = 12;
 template <int TC>
 struct TileGeom {
     static constexpr int P = TC + HALO_L + HALO_R;      // floats per smem row
-    static constexpr int GROUPS = P / 4;
     static_assert(((P / 4) & 1) == 1, "P/4 must be odd for conflict-free 128-bit row-strided access");
     static constexpr int SMEM_BYTES = TILE_B * P * 4;
 };

@@ -21,7 +21,6 @@ namespace {
 using namespace ksp;
 
 constexpr int SEL_THREADS = 1024;
-constexpr int SMEM_KEY_CAP = 49152;  // 192 KB of keys + 32 KB histogram + misc < 227 KB
 
 __device__ __forceinline__ uint32_t mad_key(float v)
 {
