@@ -217,6 +217,17 @@ class DeviceArray:
         self.context = context
         self.buffer = context.allocate(padded_shape, dtype, raw)
 
+    @classmethod
+    def wrap(cls, context: cuda.Context, ptr: int, shape: Tuple[int, ...], dtype: Any,
+             padded_shape: Optional[Tuple[int, ...]] = None, owner: Any = None) -> "DeviceArray":
+        """A ``DeviceArray`` over device memory that already exists (extension: zero-copy hand-over
+        from a GPU producer, e.g. ``DeviceArray.wrap(ctx, t.data_ptr(), t.shape, np.complex64,
+        owner=t)`` for a torch tensor).  ``owner`` is kept alive as long as the array."""
+        padded = tuple(shape) if padded_shape is None else tuple(padded_shape)
+        n_bytes = int(np.prod(padded, dtype=np.int64)) * np.dtype(dtype).itemsize
+        raw = cuda.ExternalAllocation(ptr, n_bytes, context.device.index, owner)
+        return cls(context, shape, dtype, padded, raw=raw)
+
     @property
     def shape(self) -> Tuple[int, ...]:
         return self._shape

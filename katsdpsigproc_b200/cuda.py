@@ -20,6 +20,7 @@ from typing import Any, List, Optional, Sequence, Tuple
 import numpy as np
 
 from . import _capi
+from .abc import AbstractCommandQueue, AbstractContext, AbstractDevice, AbstractEvent
 
 
 class RawAllocation:
@@ -44,6 +45,23 @@ class RawAllocation:
                 _capi.load().ksp_free(c_void_p(ptr))
             except Exception:  # interpreter shutdown
                 pass
+
+
+class ExternalAllocation:
+    """Device memory owned by someone else (a torch / cupy tensor, another library).
+
+    Has the interface of :class:`RawAllocation`, so it can back a ``DeviceArray`` through the
+    ``raw=`` argument without a copy; ``owner`` is only kept alive, never freed here.
+    """
+
+    def __init__(self, ptr: int, n_bytes: int, device_index: int = 0, owner: Any = None) -> None:
+        self.ptr = int(ptr)
+        self.n_bytes = int(n_bytes)
+        self.device_index = device_index
+        self.owner = owner
+
+    def __int__(self) -> int:
+        return self.ptr
 
 
 class DeviceBuffer:
@@ -89,7 +107,7 @@ class _PinnedBlock:
                 pass
 
 
-class Event:
+class Event(AbstractEvent):
     """A marker in a command queue (reference ``cuda.py:71-84``)."""
 
     def __init__(self, stream: int, device_index: int) -> None:
@@ -123,7 +141,7 @@ class Event:
                 pass
 
 
-class Device:
+class Device(AbstractDevice):
     """One CUDA device (reference ``cuda.py:86-158``)."""
 
     def __init__(self, index: int) -> None:
@@ -181,7 +199,7 @@ class Device:
         return [cls.get_devices()]
 
 
-class Context:
+class Context(AbstractContext):
     """Allocation and queue factory for one device (reference ``cuda.py:163-255``).
 
     The CUDA runtime's primary context of the device is used, so a ``Context``
@@ -239,7 +257,7 @@ class Context:
 
 
 
-class CommandQueue:
+class CommandQueue(AbstractCommandQueue):
     """An in-order stream (reference ``cuda.py:257-479``)."""
 
     def __init__(self, context: Context) -> None:

@@ -216,3 +216,13 @@ def test_missing_library_is_loud(monkeypatch):
     monkeypatch.setattr(_capi, "LIB_PATH", "/nonexistent/libksp_b200.so")
     with pytest.raises(ImportError, match="no CPU fallback"):
         _capi.load()
+
+
+def test_backend_implements_the_abstract_interfaces():
+    from katsdpsigproc_b200 import abc, cuda
+
+    for concrete, interface in ((cuda.Event, abc.AbstractEvent), (cuda.Device, abc.AbstractDevice),
+                                (cuda.Context, abc.AbstractContext),
+                                (cuda.CommandQueue, abc.AbstractCommandQueue)):
+        assert issubclass(concrete, interface)
+        assert not getattr(concrete, "__abstractmethods__", None), concrete.__abstractmethods__

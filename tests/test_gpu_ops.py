@@ -358,3 +358,21 @@ def test_streaming_flagger(context, abs_mode, depth, use_flags):
         np.testing.assert_array_equal(want, got)
     with pytest.raises(TypeError):
         stream.submit(dumps[0], None if use_flags else np.zeros(channels, np.uint8))
+
+
+def test_wrap_external_device_memory(context, command_queue, abs_mode):
+    """Zero-copy hand-over: bind a torch tensor's memory as the flagger's vis buffer."""
+    torch = pytest.importorskip("torch")
+    vis, spikes, _ = flagger_case(256, 64)
+    t = torch.from_numpy(vis.view(np.float32).reshape(256, 64, 2)).cuda()
+    template = rfi.FlaggerDeviceTemplate(
+        rfi.BackgroundMedianFilterDeviceTemplate(context, 13, abs_mode=abs_mode),
+        rfi.NoiseEstMADTDeviceTemplate(context, 10240),
+        rfi.ThresholdSumDeviceTemplate(context, n_windows=4))
+    fn = template.instantiate(command_queue, 256, 64, threshold_args={"n_sigma": 11.0})
+    slot = fn.slots["vis"]
+    assert slot.required_padded_shape() == (256, 64)
+    torch.cuda.synchronize()
+    wrapped = DeviceArray.wrap(context, t.data_ptr(), (256, 64), np.complex64, owner=t)
+    fn(vis=wrapped)
+    np.testing.assert_array_equal(spikes.astype(np.uint8), fn.buffer("flags").get(command_queue))
