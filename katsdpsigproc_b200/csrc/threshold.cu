@@ -18,6 +18,10 @@
 //   * mapping: one thread per run of 32 consecutive channels, one block per span of
 //     T * 32 channels of one baseline (spans overlap by the reach of the largest window,
 //     128 channels, so blocks are independent and small: several per SM);
+//   * staging: ONE TMA tile load per block (cp.async.bulk.tensor over dev_t viewed as
+//     [baseline][run][32 floats], 128-byte swizzle, hardware zero fill outside the band,
+//     completion on an mbarrier) puts the span in shared memory; plain vector loads into the
+//     same layout when the shape does not allow a tensor map;
 //   * every thread publishes its 32 flags and three statistics of its run (maximum of the
 //     first 8 samples, sum of the positive samples, sum of |u|) in shared memory;
 //   * window size 2^w, thread by thread, cheapest test first:
@@ -35,14 +39,19 @@
 //     rebuilds u and the running sums, and goes on.
 // Non-finite samples make the sums non-finite: every window within reach is then a survivor.
 #include "common.cuh"
+#include "tma.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace {
 
 using namespace ksp;
 
 constexpr int RUN = 32;
-constexpr int PITCH = 36;            // floats per staged run: 128-bit accesses one run apart are conflict-free
+// The staged span is an array of 128-byte runs in the layout TMA's 128-byte swizzle produces:
+// 16-byte chunk c of run r lives at chunk (c ^ (r & 7)).  Eight consecutive threads reading
+// "their" chunk i thus touch eight different bank groups, with no padding.
+constexpr int PITCH = 32;
 constexpr int TS_MAX_THREADS = 256;
 constexpr int TS_MAX_WINDOWS = 7;    // windows up to 64 = two runs of reach
 constexpr unsigned FULL = 0xffffffffu;
@@ -57,6 +66,7 @@ struct TsArgs {
     int64_t dev_stride, out_stride;   // out_stride: bytes per row, or words per row when packed
     int n_windows;
     int flag_value;
+    int use_tma;           // stage the span with one TMA tile load (needs tmap)
     int chunk_valid;       // channels produced per block (multiple of 32)
     int edge;              // halo on each side of a span (multiple of 32; 0 when one block per row)
     double n_sigma;
@@ -72,6 +82,14 @@ __device__ __forceinline__ uint32_t bit_range(int64_t lo, int64_t hi)
     uint32_t upto_hi = (hi == 32) ? FULL : ((1u << (int) hi) - 1u);
     return upto_hi & ~((1u << (int) lo) - 1u);
 }
+
+// float offset of element q of the staged span / of chunk i of run r (swizzled layout)
+__device__ __forceinline__ int span_offset(int q)
+{
+    const int r = q >> 5;
+    return (r << 5) + ((((q >> 2) & 7) ^ (r & 7)) << 2) + (q & 3);
+}
+__device__ __forceinline__ int chunk_offset(int r, int i) { return (r << 5) + ((i ^ (r & 7)) << 2); }
 
 // Exact evaluation of the candidate windows of one thread (rare, divergent): D_w[i] in tree
 // order from the staged row and the published flags.
@@ -92,7 +110,7 @@ __device__ __noinline__ uint32_t exact_windows(uint32_t cand, int run_index, int
             if (q < span) {
                 const bool fl = (Fsm[q >> 5] >> (q & 31)) & 1u;
                 n_flagged += fl;
-                v = fl ? 0.0f : rowbuf[q + 4 * (q >> 5)];
+                v = fl ? 0.0f : rowbuf[span_offset(q)];
             }
             vals[i] = v;
         }
@@ -103,13 +121,13 @@ __device__ __noinline__ uint32_t exact_windows(uint32_t cand, int run_index, int
     return fire;
 }
 
-// Running sums p[0..32] of one staged run with its flagged samples zeroed (rare path).
-__device__ __forceinline__ void run_sums(const float *x, uint32_t F, float (&p)[RUN + 1])
+// Running sums p[0..32] of staged run r with its flagged samples zeroed (rare path).
+__device__ __forceinline__ void run_sums(const float *rowbuf, int r, uint32_t F, float (&p)[RUN + 1])
 {
     p[0] = 0.0f;
 #pragma unroll
     for (int k = 0; k < RUN / 4; k++) {
-        const float4 q = *reinterpret_cast<const float4 *>(x + 4 * k);
+        const float4 q = *reinterpret_cast<const float4 *>(rowbuf + chunk_offset(r, k));
         const float v[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -120,18 +138,18 @@ __device__ __forceinline__ void run_sums(const float *x, uint32_t F, float (&p)[
 }
 
 // Candidate windows of size W (2..64) that start in this thread's run (rare path).
-//   x0        the staged samples of the own run; the next two runs follow PITCH and
-//             2 * PITCH floats further on (zeros beyond the span)
+//   rowbuf, r the staged span and the own run's index; runs r + 1, r + 2 exist (zeros
+//             beyond the span)
 //   F, F1, F2 flag words of the three runs;  tw = thr_w;  err = bound on |S~ - D_w|
 // The running sums are formed exactly as the kernel's rebuild() forms them.
 template <int W>
-__device__ __noinline__ uint32_t window_candidates(const float *x0, uint32_t F, uint32_t F1,
-                                                   uint32_t F2, float tw, float err)
+__device__ __noinline__ uint32_t window_candidates(const float *rowbuf, int r, uint32_t F,
+                                                   uint32_t F1, uint32_t F2, float tw, float err)
 {
     float p[RUN + 1], p1[RUN + 1], p2[RUN + 1];
-    run_sums(x0, F, p);
-    run_sums(x0 + PITCH, F1, p1);
-    if (W > RUN) run_sums(x0 + 2 * PITCH, F2, p2);
+    run_sums(rowbuf, r, F, p);
+    run_sums(rowbuf, r + 1, F1, p1);
+    if (W > RUN) run_sums(rowbuf, r + 2, F2, p2);
     else p2[0] = 0.0f;
     const bool any_flag = (F | F1 | F2) != 0u;
     const float t_full = tw * (float) W;                   // exact: W is a power of two
@@ -161,9 +179,11 @@ __device__ __noinline__ uint32_t window_candidates(const float *x0, uint32_t F, 
 // immediate offsets.
 template <bool PACKED, int TFIX>
 __global__ void __launch_bounds__(TFIX ? TFIX : TS_MAX_THREADS, TFIX ? 6 : 4)
-threshold_sum_kernel(const TsArgs a)
+threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
 {
-    extern __shared__ __align__(16) float sm[];
+    extern __shared__ __align__(1024) uint8_t sm_raw[];
+    // the swizzle pattern is a function of the shared-memory address: align the span to 1 KB
+    float *sm = reinterpret_cast<float *>(sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u));
     const int T = TFIX ? TFIX : (int) blockDim.x;
     const int tid = threadIdx.x;
     const int span = T * RUN;
@@ -175,6 +195,7 @@ threshold_sum_kernel(const TsArgs a)
     uint32_t *car1 = Fsm + T + 2;                              // T
     uint32_t *car2 = car1 + T;                                 // T
     float *thr = reinterpret_cast<float *>(car2 + T);          // TS_MAX_WINDOWS (+1)
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(thr + 8);    // TMA completion barrier
 
     const int64_t row = blockIdx.x;
     const int C = (int) a.channels;
@@ -189,47 +210,51 @@ threshold_sum_kernel(const TsArgs a)
     }
     for (int i = tid; i < 2 * PITCH; i += T) rowbuf[T * PITCH + i] = 0.0f;   // two runs of zeros past the span
 
-    // ---- stage the span: coalesced 128-bit loads -> padded runs (zeros outside the band)
-    const bool vec_ok = ((a.dev_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.dev_t) & 15) == 0) &&
-                        ((base & 3) == 0);
-    if (vec_ok && base >= 0 && base + span <= C) {
-        // whole span inside the band: no tests, all loads of a thread in flight together
-        const float4 *s4 = reinterpret_cast<const float4 *>(src + base) + tid;
-        float *dst = rowbuf + (tid >> 3) * PITCH + 4 * (tid & 7);
-        const int dstep = (T >> 3) * PITCH;
-#pragma unroll
-        for (int i = 0; i < RUN / 4; i++) {
-            const float4 v = __ldg(s4 + i * T);
-            *reinterpret_cast<float4 *>(dst + i * dstep) = v;
+    // ---- stage the span (zeros outside the band)
+    if (a.use_tma) {
+        // one TMA tile load: T runs of 128 bytes, swizzled, out-of-band runs zero-filled by the
+        // hardware; thread 0 issues it, everybody waits on the mbarrier
+        if (tid == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(mbar, (uint32_t) span * 4u);
+            tma_load_3d(rowbuf, &tmap, 0, base >> 5, (int) row, mbar);
         }
-    } else if (vec_ok && (C & 3) == 0) {
-        // span sticks out of the band: whole float4s are either inside or outside
-        float4 v[RUN / 4];
-#pragma unroll
-        for (int i = 0; i < RUN / 4; i++) {
-            const int g = base + 4 * (tid + i * T);
-            v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            if (g >= 0 && g < C) v[i] = __ldg(reinterpret_cast<const float4 *>(src + g));
-        }
-        float *dst = rowbuf + (tid >> 3) * PITCH + 4 * (tid & 7);
-        const int dstep = (T >> 3) * PITCH;
-#pragma unroll
-        for (int i = 0; i < RUN / 4; i++) *reinterpret_cast<float4 *>(dst + i * dstep) = v[i];
+        mbar_wait(mbar, 0);
     } else {
-        for (int q = tid; q < (span >> 2); q += T) {
-            const int p = q << 2;
-            const int g = base + p;
-            float4 v;
-            v.x = (g >= 0 && g < C) ? src[g] : 0.0f;
-            v.y = (g + 1 >= 0 && g + 1 < C) ? src[g + 1] : 0.0f;
-            v.z = (g + 2 >= 0 && g + 2 < C) ? src[g + 2] : 0.0f;
-            v.w = (g + 3 >= 0 && g + 3 < C) ? src[g + 3] : 0.0f;
-            *reinterpret_cast<float4 *>(rowbuf + p + 4 * (p >> 5)) = v;
+        const bool vec_ok = ((a.dev_stride & 3) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(a.dev_t) & 15) == 0) && ((base & 3) == 0) &&
+                            ((C & 3) == 0);
+        if (vec_ok) {
+            // all loads of a thread in flight together, then the swizzled stores
+            float4 v[RUN / 4];
+#pragma unroll
+            for (int i = 0; i < RUN / 4; i++) {
+                const int g = base + ((tid + i * T) << 2);
+                v[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (g >= 0 && g < C) v[i] = __ldg(reinterpret_cast<const float4 *>(src + g));
+            }
+#pragma unroll
+            for (int i = 0; i < RUN / 4; i++) {
+                const int q = tid + i * T;                       // 16-byte chunk of the span
+                *reinterpret_cast<float4 *>(rowbuf + chunk_offset(q >> 3, q & 7)) = v[i];
+            }
+        } else {
+            for (int q = tid; q < (span >> 2); q += T) {
+                const int g = base + (q << 2);
+                float4 v;
+                v.x = (g >= 0 && g < C) ? src[g] : 0.0f;
+                v.y = (g + 1 >= 0 && g + 1 < C) ? src[g + 1] : 0.0f;
+                v.z = (g + 2 >= 0 && g + 2 < C) ? src[g + 2] : 0.0f;
+                v.w = (g + 3 >= 0 && g + 3 < C) ? src[g + 3] : 0.0f;
+                *reinterpret_cast<float4 *>(rowbuf + chunk_offset(q >> 3, q & 7)) = v;
+            }
         }
+        __syncthreads();
     }
-    __syncthreads();
 
     // ---- my run: window size 1, then running sums of what is left
+    const int my_sw = tid & 7;                                 // swizzle of my run
     const float *my = rowbuf + tid * PITCH;
     const int64_t pos0 = (int64_t) base + (int64_t) tid * RUN;  // row channel of element 0
     const uint32_t in_range = bit_range(-pos0, (int64_t) C - pos0);
@@ -242,7 +267,7 @@ threshold_sum_kernel(const TsArgs a)
         float x[RUN];
 #pragma unroll
         for (int i = 0; i < RUN / 4; i++) {
-            const float4 v = *reinterpret_cast<const float4 *>(my + 4 * i);
+            const float4 v = *reinterpret_cast<const float4 *>(my + ((i ^ my_sw) << 2));
             x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
         }
         if (first) {
@@ -343,12 +368,12 @@ threshold_sum_kernel(const TsArgs a)
                 const uint32_t G2 = two ? F2 : 0u;
                 uint32_t cand;
                 switch (w) {
-                case 1: cand = window_candidates<2>(my, F, F1, G2, tw, err); break;
-                case 2: cand = window_candidates<4>(my, F, F1, G2, tw, err); break;
-                case 3: cand = window_candidates<8>(my, F, F1, G2, tw, err); break;
-                case 4: cand = window_candidates<16>(my, F, F1, G2, tw, err); break;
-                case 5: cand = window_candidates<32>(my, F, F1, G2, tw, err); break;
-                default: cand = window_candidates<64>(my, F, F1, G2, tw, err); break;
+                case 1: cand = window_candidates<2>(rowbuf, tid, F, F1, G2, tw, err); break;
+                case 2: cand = window_candidates<4>(rowbuf, tid, F, F1, G2, tw, err); break;
+                case 3: cand = window_candidates<8>(rowbuf, tid, F, F1, G2, tw, err); break;
+                case 4: cand = window_candidates<16>(rowbuf, tid, F, F1, G2, tw, err); break;
+                case 5: cand = window_candidates<32>(rowbuf, tid, F, F1, G2, tw, err); break;
+                default: cand = window_candidates<64>(rowbuf, tid, F, F1, G2, tw, err); break;
                 }
                 cand &= hot;
                 if (cand != 0u) fire = exact_windows(cand, tid, w, tw, rowbuf, Fsm, span);
@@ -514,7 +539,8 @@ expand_flags_kernel(const uint32_t *__restrict__ bits_t, uint8_t *__restrict__ f
 
 size_t ts_smem_bytes(int threads)
 {
-    return sizeof(float) * (((size_t) threads + 2) * PITCH + 7 * ((size_t) threads + 2) + 16);
+    // + 1 KB so that the span can be aligned for the swizzle, + the mbarrier
+    return sizeof(float) * (((size_t) threads + 2) * PITCH + 7 * ((size_t) threads + 2) + 16) + 1024 + 16;
 }
 
 int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise, uint8_t *flags_t,
@@ -567,13 +593,34 @@ int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise,
     if (n_chunks > 65535) return KSP_ETOOLARGE;
     dim3 grid((unsigned) baselines, (unsigned) n_chunks);
     const size_t smem = ts_smem_bytes(threads);
+    // TMA staging: dev_t viewed as [baselines][channels / 32][32] floats, box = [1][threads][32],
+    // 128-byte swizzle, zero fill outside the tensor (needs whole runs and 16-byte alignment)
+    CUtensorMap tmap;
+    memset(&tmap, 0, sizeof(tmap));
+    a.use_tma = 0;
+    static const bool tma_allowed = [] {
+        const char *e = getenv("KSP_TS_TMA");
+        return !(e && atoi(e) == 0);
+    }();
+    if (tma_allowed && (channels % RUN) == 0 && (dev_stride % 4) == 0 &&
+        ((uintptr_t) dev_t % 16) == 0 && threads <= 256 && tensor_map_encoder()) {
+        const cuuint64_t dims[3] = {(cuuint64_t) RUN, (cuuint64_t) (channels / RUN), (cuuint64_t) baselines};
+        const cuuint64_t strides[2] = {RUN * sizeof(float), (cuuint64_t) dev_stride * sizeof(float)};
+        const cuuint32_t box[3] = {RUN, (cuuint32_t) threads, 1};
+        const cuuint32_t elem[3] = {1, 1, 1};
+        CUresult rc = tensor_map_encoder()(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *) dev_t, dims,
+                                           strides, box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        a.use_tma = (rc == CUDA_SUCCESS) ? 1 : 0;
+    }
     // (the largest block needs less than the default 48 KB of dynamic shared memory)
     if (bits_t) {
-        if (threads == 128) threshold_sum_kernel<true, 128><<<grid, threads, smem, s>>>(a);
-        else threshold_sum_kernel<true, 0><<<grid, threads, smem, s>>>(a);
+        if (threads == 128) threshold_sum_kernel<true, 128><<<grid, threads, smem, s>>>(a, tmap);
+        else threshold_sum_kernel<true, 0><<<grid, threads, smem, s>>>(a, tmap);
     } else {
-        if (threads == 128) threshold_sum_kernel<false, 128><<<grid, threads, smem, s>>>(a);
-        else threshold_sum_kernel<false, 0><<<grid, threads, smem, s>>>(a);
+        if (threads == 128) threshold_sum_kernel<false, 128><<<grid, threads, smem, s>>>(a, tmap);
+        else threshold_sum_kernel<false, 0><<<grid, threads, smem, s>>>(a, tmap);
     }
     KSP_CHECK_LAUNCH();
     return 0;
