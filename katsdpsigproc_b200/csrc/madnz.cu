@@ -80,6 +80,9 @@ __device__ void block_median_keys(const KeySource &key_at, int n, uint32_t n_val
 constexpr int MS_THREADS = 256;
 constexpr int MS_SLOTS = 38;              // list slots per thread (mean use ~16 of 128 keys)
 constexpr int MS_BINS = 2048;
+#ifndef MS_UNROLL
+#define MS_UNROLL 8                       // float4 loads in flight per thread (multiple of 4)
+#endif
 constexpr int MS_SMALL_CAP = 32;
 constexpr uint32_t KEY_INF = 0x7f800000u;
 static_assert(MS_SLOTS * MS_THREADS >= SELECT_HIST_WORDS, "the fallback's histogram aliases the lists");
@@ -98,22 +101,75 @@ __device__ __forceinline__ uint32_t sort32(uint32_t v, int lane)
     return v;
 }
 
-struct StreamState {
-    uint32_t nv, below, n;   // usable keys, keys below LO, keys kept (may exceed MS_SLOTS)
-    uint32_t *slot;          // next free slot of this thread's list
-};
-
-__device__ __forceinline__ void stream_key(float x, uint32_t lo, uint32_t lo_m1, uint32_t width,
-                                           StreamState &st)
+// N independent bitonic sorts across the warp, interleaved so that the shuffle latencies overlap
+template <int N>
+__device__ __forceinline__ void sort32xN(uint32_t (&v)[N], int lane)
 {
-    const uint32_t key = __float_as_uint(x) & 0x7fffffffu;
-    const uint32_t km1 = key - 1u;                 // zero wraps to the top: never counted
-    st.nv += (km1 < KEY_INF) ? 1u : 0u;
-    st.below += (km1 < lo_m1) ? 1u : 0u;
-    if (key - lo < width) {
-        if (st.n < (uint32_t) MS_SLOTS) *st.slot = key;
-        st.slot += MS_THREADS;
-        st.n++;
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool keep_min = ((lane & k) == 0) == ((lane & j) == 0);
+#pragma unroll
+            for (int g = 0; g < N; g++) {
+                const uint32_t other = __shfl_xor_sync(0xffffffffu, v[g], j);
+                v[g] = keep_min ? min(v[g], other) : max(v[g], other);
+            }
+        }
+    }
+}
+
+// warp-inclusive prefix sum
+__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// One element of the pass, branch-free (7 instructions): three float compares with |x| as an
+// operand modifier, two predicated counters and a predicated append of the RAW bits (readers
+// of the lists mask the sign).  In positive-float order these are exactly the integer key
+// tests: usable <=> |x| > 0 (false for zero and NaN), and the bracket is LO <= |x| <= HI.
+// `slot` is the shared-space byte address of the thread's next free list slot.
+__device__ __forceinline__ void stream_key_fast(float x, float lo_f, float hi_f, uint32_t &nv,
+                                                uint32_t &ge, uint32_t &slot)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p0, p2, p3;\n\t"
+        ".reg .f32 ax;\n\t"
+        "abs.f32 ax, %3;\n\t"
+        "setp.gt.f32 p0, ax, 0f00000000;\n\t"
+        "setp.ge.f32 p2, ax, %4;\n\t"
+        "setp.le.and.f32 p3, ax, %5, p2;\n\t"
+        "@p0 add.u32 %0, %0, 1;\n\t"
+        "@p2 add.u32 %1, %1, 1;\n\t"
+        "@p3 st.shared.f32 [%2], %3;\n\t"
+        "@p3 add.u32 %2, %2, %6;\n\t"
+        "}"
+        : "+r"(nv), "+r"(ge), "+r"(slot)
+        : "f"(x), "f"(lo_f), "f"(hi_f), "n"(MS_THREADS * 4));
+}
+
+// The same with a capacity check, for batches that might fill the list and for the row tail.
+__device__ __forceinline__ void stream_key_checked(float x, float lo_f, float hi_f, uint32_t &nv,
+                                                   uint32_t &ge, uint32_t &slot, uint32_t slot_end,
+                                                   bool &over)
+{
+    const float ax = fabsf(x);
+    nv += (ax > 0.0f) ? 1u : 0u;
+    ge += (ax >= lo_f) ? 1u : 0u;
+    if (ax >= lo_f && ax <= hi_f) {
+        if (slot < slot_end) {
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot), "f"(x));
+            slot += MS_THREADS * 4;
+        } else {
+            over = true;
+        }
     }
 }
 
@@ -123,100 +179,135 @@ madnz_stream_kernel(const float *__restrict__ dev_t, float *__restrict__ noise, 
 {
     __shared__ __align__(16) uint32_t lists[MS_SLOTS * MS_THREADS];
     __shared__ __align__(16) uint32_t hist[MS_BINS];
+    __shared__ uint32_t coarse[MS_BINS / 32];        // sums of 32 consecutive bins of hist
     __shared__ uint32_t misc[160];
-    // misc: 0 nv, 1 below, 2 overflow flag, 3 bin, 4 count before bin, 5 count in bin, 6 LO,
-    //       7 HI, 8 small count, 9 count <= v1 in lists, 10 min above v1, 11 v1, 12 kept total,
-    //       16..63 scan / fallback scratch, 64..95 group lows, 96..127 group highs,
+    // misc: 0 nv, 1 below, 2 overflow flag, 8 small count, 10 min key beyond the wanted bin,
+    //       12 kept total, 16..63 fallback scratch, 64..95 group lows, 96..127 group highs,
     //       128..159 small list
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int NWARPS = MS_THREADS / 32;
     const float *row = dev_t + (int64_t) blockIdx.x * stride;
 
     for (int i = tid; i < MS_BINS; i += MS_THREADS) hist[i] = 0u;
+    if (tid < MS_BINS / 32) coarse[tid] = 0u;
     if (tid < 16) misc[tid] = (tid == 10) ? 0xffffffffu : 0u;
 
-    // ---- 1. bracket
+    // ---- 1. bracket: all four sample loads in flight together, then four interleaved sorts;
+    //         every warp reduces the 32 group quantiles itself (no second barrier)
+    uint32_t lo, hi;
     {
         const int step = channels >> 10;
+        uint32_t key[4];
 #pragma unroll
         for (int g = 0; g < 4; g++) {
             const int i = tid * 4 + g;                                   // sample number, 0..1023
             int pos = (int) (((int64_t) i * channels) >> 10);
             if (step > 1) pos += (int) (((uint32_t) i * 2654435761u) >> 16) % step;
-            uint32_t key = 0xffffffffu;
-            if (channels > 0) {
-                const uint32_t k = __float_as_uint(row[min(pos, channels - 1)]) & 0x7fffffffu;
-                if ((k - 1u) < KEY_INF) key = k;
-            }
-            // group = the g-th samples of this warp's lanes
-            const bool valid = key != 0xffffffffu;
-            const uint32_t sorted = sort32(key, lane);
-            const int m = __popc(__ballot_sync(0xffffffffu, valid));
-            const uint32_t lo_g = __shfl_sync(0xffffffffu, sorted, (m * 14) >> 5);
-            const uint32_t hi_g = __shfl_sync(0xffffffffu, sorted, min(max(m - 1, 0), (m * 18 + 31) >> 5));
+            key[g] = (channels > 0) ? __float_as_uint(__ldg(row + min(pos, channels - 1))) : 0u;
+        }
+        int m[4];
+#pragma unroll
+        for (int g = 0; g < 4; g++) {                 // group g = the g-th samples of the warp's lanes
+            const uint32_t k = key[g] & 0x7fffffffu;
+            key[g] = ((k - 1u) < KEY_INF) ? k : 0xffffffffu;
+            m[g] = __popc(__ballot_sync(0xffffffffu, key[g] != 0xffffffffu));
+        }
+        sort32xN<4>(key, lane);
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint32_t lo_g = __shfl_sync(0xffffffffu, key[g], (m[g] * 14) >> 5);
+            const uint32_t hi_g = __shfl_sync(0xffffffffu, key[g],
+                                              min(max(m[g] - 1, 0), (m[g] * 18 + 31) >> 5));
             if (lane == 0) {
-                misc[64 + warp * 4 + g] = m ? lo_g : 0xffffffffu;
-                misc[96 + warp * 4 + g] = m ? hi_g : 0xffffffffu;
+                misc[64 + warp * 4 + g] = m[g] ? lo_g : 0xffffffffu;
+                misc[96 + warp * 4 + g] = m[g] ? hi_g : 0xffffffffu;
             }
         }
         __syncthreads();
-        if (warp < 2) {
-            const uint32_t v = misc[64 + 32 * warp + lane];
-            const uint32_t s = sort32(v, lane);
-            const int cnt = __popc(__ballot_sync(0xffffffffu, v != 0xffffffffu));
-            const uint32_t pick = __shfl_sync(0xffffffffu, s, warp ? cnt >> 1 : (max(cnt, 1) - 1) >> 1);
-            if (lane == 0) misc[6 + warp] = cnt ? pick : (warp ? KEY_INF : 1u);
-        }
-        __syncthreads();
+        uint32_t q[2] = {misc[64 + lane], misc[96 + lane]};
+        const int cnt_lo = __popc(__ballot_sync(0xffffffffu, q[0] != 0xffffffffu));
+        const int cnt_hi = __popc(__ballot_sync(0xffffffffu, q[1] != 0xffffffffu));
+        sort32xN<2>(q, lane);
+        lo = __shfl_sync(0xffffffffu, q[0], (max(cnt_lo, 1) - 1) >> 1);
+        hi = __shfl_sync(0xffffffffu, q[1], cnt_hi >> 1);
+        if (cnt_lo == 0) lo = 1u;
+        if (cnt_hi == 0) hi = KEY_INF;
+        hi = max(hi, lo);
     }
-    const uint32_t lo = misc[6];
-    const uint32_t hi = max(misc[7], lo);
     const uint32_t width = hi - lo + 1u;
 
     // ---- 2. the one pass over the row
     uint32_t n_mine;
     {
-        StreamState st = {0u, 0u, 0u, lists + tid};
-        const uint32_t lo_m1 = lo - 1u;
+        const float lo_f = __uint_as_float(lo), hi_f = __uint_as_float(hi);
+        const uint32_t slot0 = (uint32_t) __cvta_generic_to_shared(lists + tid);
+        const uint32_t slot_end = slot0 + MS_SLOTS * MS_THREADS * 4;
+        constexpr uint32_t BATCH_BYTES = 16 * MS_THREADS * 4;   // 16 appends
+        uint32_t nv = 0, ge = 0, slot = slot0;
+        bool over = false;
         if (((stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(dev_t) & 15) == 0)) {
             const float4 *row4 = reinterpret_cast<const float4 *>(row);
             const int n4 = channels >> 2;
             int i = tid;
-            for (; i + 3 * MS_THREADS < n4; i += 4 * MS_THREADS) {
-                float4 v[4];
+            for (; i + (MS_UNROLL - 1) * MS_THREADS < n4; i += MS_UNROLL * MS_THREADS) {
+                float4 v[MS_UNROLL];
 #pragma unroll
-                for (int u = 0; u < 4; u++) v[u] = __ldg(row4 + i + u * MS_THREADS);
+                for (int u = 0; u < MS_UNROLL; u++) v[u] = __ldg(row4 + i + u * MS_THREADS);
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    stream_key(v[u].x, lo, lo_m1, width, st);
-                    stream_key(v[u].y, lo, lo_m1, width, st);
-                    stream_key(v[u].z, lo, lo_m1, width, st);
-                    stream_key(v[u].w, lo, lo_m1, width, st);
+                for (int h = 0; h < MS_UNROLL; h += 4) {
+                    if (slot + BATCH_BYTES <= slot_end) {        // room for all 16: no checks
+#pragma unroll
+                        for (int u = h; u < h + 4; u++) {
+                            stream_key_fast(v[u].x, lo_f, hi_f, nv, ge, slot);
+                            stream_key_fast(v[u].y, lo_f, hi_f, nv, ge, slot);
+                            stream_key_fast(v[u].z, lo_f, hi_f, nv, ge, slot);
+                            stream_key_fast(v[u].w, lo_f, hi_f, nv, ge, slot);
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = h; u < h + 4; u++) {
+                            stream_key_checked(v[u].x, lo_f, hi_f, nv, ge, slot, slot_end, over);
+                            stream_key_checked(v[u].y, lo_f, hi_f, nv, ge, slot, slot_end, over);
+                            stream_key_checked(v[u].z, lo_f, hi_f, nv, ge, slot, slot_end, over);
+                            stream_key_checked(v[u].w, lo_f, hi_f, nv, ge, slot, slot_end, over);
+                        }
+                    }
                 }
             }
             for (; i < n4; i += MS_THREADS) {
                 const float4 v = __ldg(row4 + i);
-                stream_key(v.x, lo, lo_m1, width, st);
-                stream_key(v.y, lo, lo_m1, width, st);
-                stream_key(v.z, lo, lo_m1, width, st);
-                stream_key(v.w, lo, lo_m1, width, st);
+                stream_key_checked(v.x, lo_f, hi_f, nv, ge, slot, slot_end, over);
+                stream_key_checked(v.y, lo_f, hi_f, nv, ge, slot, slot_end, over);
+                stream_key_checked(v.z, lo_f, hi_f, nv, ge, slot, slot_end, over);
+                stream_key_checked(v.w, lo_f, hi_f, nv, ge, slot, slot_end, over);
             }
             for (int j = (n4 << 2) + tid; j < channels; j += MS_THREADS)
-                stream_key(row[j], lo, lo_m1, width, st);
+                stream_key_checked(row[j], lo_f, hi_f, nv, ge, slot, slot_end, over);
         } else {
-            for (int j = tid; j < channels; j += MS_THREADS) stream_key(row[j], lo, lo_m1, width, st);
+            for (int j = tid; j < channels; j += MS_THREADS)
+                stream_key_checked(row[j], lo_f, hi_f, nv, ge, slot, slot_end, over);
         }
-        n_mine = st.n;
-        const uint32_t nv = __reduce_add_sync(0xffffffffu, st.nv);
-        const uint32_t below = __reduce_add_sync(0xffffffffu, st.below);
-        const uint32_t kept = __reduce_add_sync(0xffffffffu, st.n);
-        const bool over = __any_sync(0xffffffffu, st.n > (uint32_t) MS_SLOTS);
+        n_mine = (slot - slot0) / (MS_THREADS * 4);
+        const uint32_t nv_w = __reduce_add_sync(0xffffffffu, nv);
+        const uint32_t below_w = __reduce_add_sync(0xffffffffu, nv - ge);
+        const uint32_t kept_w = __reduce_add_sync(0xffffffffu, n_mine);
+        const bool over_w = __any_sync(0xffffffffu, over);
         if (lane == 0) {
-            atomicAdd(&misc[0], nv);
-            atomicAdd(&misc[1], below);
-            atomicAdd(&misc[12], kept);
-            if (over) misc[2] = 1u;
+            atomicAdd(&misc[0], nv_w);
+            atomicAdd(&misc[1], below_w);
+            atomicAdd(&misc[12], kept_w);
+            if (over_w) misc[2] = 1u;
         }
+    }
+
+    // ---- 3. select inside the lists.  Histogram of the kept keys at two levels (2048 bins and
+    //         their sums in groups of 32), so that after ONE barrier every warp can locate the
+    //         wanted bin by itself with two warp scans.
+    const uint32_t *mine = lists + tid;
+    const int shift = (width <= (uint32_t) MS_BINS) ? 0 : (32 - __clz(width - 1u)) - 11;
+    for (uint32_t k = 0; k < n_mine; k++) {
+        const uint32_t b = ((mine[k * MS_THREADS] & 0x7fffffffu) - lo) >> shift;
+        atomicAdd(&hist[b], 1u);
+        atomicAdd(&coarse[b >> 5], 1u);
     }
     __syncthreads();
     const uint32_t n_valid = misc[0];
@@ -224,104 +315,74 @@ madnz_stream_kernel(const float *__restrict__ dev_t, float *__restrict__ noise, 
         if (tid == 0) noise[blockIdx.x] = __int_as_float(0x7fc00000);
         return;
     }
+    const bool even = !(n_valid & 1u);
     const uint32_t rank = (n_valid - 1u) >> 1;                // lower median, 0-based
     const uint32_t r_rel = rank - misc[1];                    // rank inside the lists (wraps if below)
-    bool fallback = (misc[2] != 0u) || (r_rel >= misc[12]);
-    const uint32_t *mine = lists + tid;
+    const uint32_t kept = misc[12];
+    // the bracket must hold the lower median and, for an even count, the key after it
+    bool fallback = (misc[2] != 0u) || (r_rel >= kept) || (even && r_rel + 1u >= kept);
 
-    uint32_t v1 = 0, v2 = 0;
-    if (!fallback) {
-        // ---- 3. select rank r_rel among the kept keys
-        const int shift = (width <= (uint32_t) MS_BINS) ? 0 : (32 - __clz(width - 1u)) - 11;
-        for (uint32_t k = 0; k < n_mine; k++)
-            atomicAdd(&hist[(mine[k * MS_THREADS] - lo) >> shift], 1u);
-        __syncthreads();
-        {
-            constexpr int BPT = MS_BINS / MS_THREADS;         // 8 bins per thread
-            uint32_t h[BPT], own = 0;
-#pragma unroll
-            for (int k = 0; k < BPT; k++) {
-                h[k] = hist[tid * BPT + k];
-                own += h[k];
-            }
-            uint32_t incl = own;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-                if (lane >= d) incl += o;
-            }
-            if (lane == 31) misc[16 + warp] = incl;
-            __syncthreads();
-            const uint32_t w = (lane < NWARPS) ? misc[16 + lane] : 0u;
-            uint32_t cum = __reduce_add_sync(0xffffffffu, lane < warp ? w : 0u) + incl - own;
-            if (r_rel >= cum && r_rel < cum + own) {
-#pragma unroll
-                for (int k = 0; k < BPT; k++) {
-                    if (r_rel >= cum && r_rel < cum + h[k]) {
-                        misc[3] = (uint32_t) (tid * BPT + k);
-                        misc[4] = cum;
-                        misc[5] = h[k];
-                    }
-                    cum += h[k];
-                }
-            }
+    if (!fallback) {                                          // block-uniform
+        // coarse level: lane owns coarse bins 2*lane, 2*lane + 1
+        const uint32_t c0 = coarse[2 * lane], c1 = coarse[2 * lane + 1];
+        const uint32_t c_incl = warp_scan_incl(c0 + c1, lane), c_excl = c_incl - (c0 + c1);
+        const int src = __ffs(__ballot_sync(0xffffffffu, r_rel >= c_excl && r_rel < c_incl)) - 1;
+        const uint32_t base = __shfl_sync(0xffffffffu, c_excl, src);
+        const uint32_t first = __shfl_sync(0xffffffffu, c0, src);
+        const bool second = r_rel >= base + first;
+        const uint32_t cbin = 2u * (uint32_t) src + (second ? 1u : 0u);
+        const uint32_t r_c = r_rel - base - (second ? first : 0u);       // rank inside the coarse bin
+        // fine level: lane owns one bin of the coarse bin
+        const uint32_t f = hist[cbin * 32u + lane];
+        const uint32_t f_incl = warp_scan_incl(f, lane), f_excl = f_incl - f;
+        const int src2 = __ffs(__ballot_sync(0xffffffffu, r_c >= f_excl && r_c < f_incl)) - 1;
+        const uint32_t bin = cbin * 32u + (uint32_t) src2;
+        const uint32_t in_bin = __shfl_sync(0xffffffffu, f, src2);
+        const uint32_t r_bin = r_c - __shfl_sync(0xffffffffu, f_excl, src2);   // rank inside the bin
+        const bool exact_bins = shift == 0;                   // a bin is one key value
+        const bool crowded = !exact_bins && in_bin > (uint32_t) MS_SMALL_CAP;
+
+        // second walk over the lists: the keys of the wanted bin, and the smallest key beyond it
+        uint32_t above = 0xffffffffu;
+        for (uint32_t k = 0; k < n_mine; k++) {
+            const uint32_t key = mine[k * MS_THREADS] & 0x7fffffffu;
+            const uint32_t b = (key - lo) >> shift;
+            if (b == bin && !exact_bins && !crowded) misc[128 + atomicAdd(&misc[8], 1u)] = key;
+            above = min(above, b > bin ? key : 0xffffffffu);
         }
+        above = __reduce_min_sync(0xffffffffu, above);
+        if (lane == 0 && above != 0xffffffffu) atomicMin(&misc[10], above);
         __syncthreads();
-        const uint32_t bin = misc[3], in_bin = misc[5];
-        const uint32_t r_bin = r_rel - misc[4];               // rank inside the bin
-        if (shift == 0) {
-            v1 = lo + bin;
-        } else if (in_bin <= (uint32_t) MS_SMALL_CAP) {
-            for (uint32_t k = 0; k < n_mine; k++) {
-                const uint32_t key = mine[k * MS_THREADS];
-                if (((key - lo) >> shift) == bin) misc[128 + atomicAdd(&misc[8], 1u)] = key;
-            }
-            __syncthreads();
-            if (warp == 0) {
-                const uint32_t s = sort32(lane < (int) in_bin ? misc[128 + lane] : 0xffffffffu, lane);
-                const uint32_t pick = __shfl_sync(0xffffffffu, s, (int) r_bin);
-                if (lane == 0) misc[11] = pick;
-            }
-            __syncthreads();
-            v1 = misc[11];
+        if (crowded) {
+            fallback = true;                                  // heavy ties: block-uniform
         } else {
-            fallback = true;                                  // crowded bin: block-uniform
+            if (warp == 0) {
+                uint32_t v1, nxt;                             // rank r_bin and r_bin + 1 inside the bin
+                if (exact_bins) {
+                    v1 = lo + bin;
+                    nxt = v1;
+                } else {
+                    const uint32_t srt = sort32(lane < (int) in_bin ? misc[128 + lane] : 0xffffffffu, lane);
+                    v1 = __shfl_sync(0xffffffffu, srt, (int) r_bin);
+                    nxt = __shfl_sync(0xffffffffu, srt, (int) min(r_bin + 1u, 31u));
+                }
+                const uint32_t v2 = !even ? v1 : (r_bin + 1u < in_bin ? nxt : misc[10]);
+                if (lane == 0) noise[blockIdx.x] = mad_finish(v1, v2);
+            }
+            return;
         }
     }
-    if (!fallback) {
-        v2 = v1;
-        if (!(n_valid & 1u)) {
-            // upper median: another copy of v1 if enough keys are <= v1, else the next key up
-            uint32_t le = 0, above = 0xffffffffu;
-            for (uint32_t k = 0; k < n_mine; k++) {
-                const uint32_t key = mine[k * MS_THREADS];
-                le += (key <= v1) ? 1u : 0u;
-                above = min(above, key > v1 ? key : 0xffffffffu);
-            }
-            le = __reduce_add_sync(0xffffffffu, le);
-            above = __reduce_min_sync(0xffffffffu, above);
-            if (lane == 0) {
-                atomicAdd(&misc[9], le);
-                atomicMin(&misc[10], above);
-            }
-            __syncthreads();
-            const uint32_t count_le = misc[1] + misc[9];
-            if (count_le < rank + 2u) {
-                v2 = misc[10];
-                if (v2 == 0xffffffffu) fallback = true;        // next key lies beyond the bracket
-            }
-        }
-    }
-    if (fallback) {
-        // ---- plain radix select over the row in global memory (rare)
+    // ---- plain radix select over the row in global memory (rare)
+    {
         __syncthreads();
+        uint32_t v1, v2;
         SelectScratch sc;
         sc.hist = lists;
         sc.misc = misc + 16;
         auto src = [row](int i) { return mad_key(row[i]); };
         block_median_keys<MS_THREADS>(src, channels, n_valid, sc, v1, v2);
+        if (tid == 0) noise[blockIdx.x] = mad_finish(v1, v2);
     }
-    if (tid == 0) noise[blockIdx.x] = mad_finish(v1, v2);
 }
 
 // ------------------------------------------------------------------ channel-major MAD

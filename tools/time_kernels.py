@@ -42,6 +42,8 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--chunks", type=str, default="0")
     ap.add_argument("--only-fused", action="store_true")
+    ap.add_argument("--tpad", type=int, default=0,
+                    help="extra elements in the row stride of the baseline-major arrays")
     args = ap.parse_args()
     C, B = args.channels, args.baselines
     dev = torch.device("cuda:0")
@@ -53,9 +55,10 @@ def main():
     del spikes
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     dev_cm = torch.empty(C, B, dtype=torch.float32, device=dev)
-    dev_t = torch.empty(B, C, dtype=torch.float32, device=dev)
+    CT = C + args.tpad                      # row stride of dev_t / flags_t
+    dev_t = torch.empty(B, CT, dtype=torch.float32, device=dev)
     noise = torch.empty(B, dtype=torch.float32, device=dev)
-    flags_t = torch.empty(B, C, dtype=torch.uint8, device=dev)
+    flags_t = torch.empty(B, CT, dtype=torch.uint8, device=dev)
     flags = torch.empty(C, B, dtype=torch.uint8, device=dev)
     N = C * B
     res = {}
@@ -71,22 +74,22 @@ def main():
             "ksp_background_median_filter", S, p(vis), p(dev_cm), None, C, B, B, B, 0, 13, 0, 0, 0),
             args.reps, flush), 12)
         rec("background_t", timeit(lambda: _capi.call(
-            "ksp_background_median_filter_t", S, p(vis), p(dev_t), None, C, B, B, C, 0, 13, 0, 0, 0),
+            "ksp_background_median_filter_t", S, p(vis), p(dev_t), None, C, B, B, CT, 0, 13, 0, 0, 0),
             args.reps, flush), 12)
         rec("transpose_f32", timeit(lambda: _capi.call(
-            "ksp_transpose", S, p(dev_t), p(dev_cm), C, B, C, B, 4), args.reps, flush), 8)
+            "ksp_transpose", S, p(dev_t), p(dev_cm), C, B, CT, B, 4), args.reps, flush), 8)
         rec("madnz_t", timeit(lambda: _capi.call(
-            "ksp_madnz_t", S, p(dev_t), p(noise), C, B, C), args.reps, flush), 4)
+            "ksp_madnz_t", S, p(dev_t), p(noise), C, B, CT), args.reps, flush), 4)
         rec("madnz", timeit(lambda: _capi.call(
             "ksp_madnz", S, p(dev_cm), p(noise), C, B, B), args.reps, flush), 4)
         rec("threshold_sum7", timeit(lambda: _capi.call(
-            "ksp_threshold_sum", S, p(dev_t), p(noise), p(flags_t), C, B, C, C, 7, c_double(11.0), sc7, 1),
+            "ksp_threshold_sum", S, p(dev_t), p(noise), p(flags_t), C, B, CT, CT, 7, c_double(11.0), sc7, 1),
             args.reps, flush), 5)
         rec("threshold_simple_t", timeit(lambda: _capi.call(
-            "ksp_threshold_simple", S, p(dev_t), p(noise), p(flags_t), B, C, C, C, c_double(11.0), 1, 1),
+            "ksp_threshold_simple", S, p(dev_t), p(noise), p(flags_t), B, C, CT, CT, c_double(11.0), 1, 1),
             args.reps, flush), 5)
         rec("transpose_u8", timeit(lambda: _capi.call(
-            "ksp_transpose", S, p(flags), p(flags_t), B, C, B, C, 1), args.reps, flush), 2)
+            "ksp_transpose", S, p(flags), p(flags_t), B, C, B, CT, 1), args.reps, flush), 2)
     print("flagged fraction", float(flags.float().mean()))
     for chunk in [int(x) for x in args.chunks.split(",")]:
         prm = cu.flagger_params(C, B, B, B, n_windows=7, chunk_baselines=chunk)
@@ -101,7 +104,7 @@ def main():
     if not args.only_fused:
         pct = torch.empty(5, B, dtype=torch.float32, device=dev)
         rec("percentile5_f32", timeit(lambda: _capi.call(
-            "ksp_percentile5", S, p(dev_t), p(pct), B, C, B, 0, C, 1, 0), args.reps, flush), 4)
+            "ksp_percentile5", S, p(dev_t), p(pct), B, CT, B, 0, C, 1, 0), args.reps, flush), 4)
         mask = (torch.rand(C, device=dev) < 0.9).float()
         dest = torch.empty(B, 2, dtype=torch.float32, device=dev)
         rec("maskedsum_c64", timeit(lambda: _capi.call(
