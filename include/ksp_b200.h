@@ -210,6 +210,11 @@ int ksp_kernel_launch_count(unsigned long long *count);
 int ksp_profile_enable(int on);
 int ksp_profile_read(double *stage_ms, int *stage_launches, int n_stages);
 
+/* Rows for which ksp_madnz_t / ksp_percentile5 had to redo the selection with the slow
+ * radix select because the sampled bracket missed the wanted rank (expected: well below
+ * 1 % of rows).  Waits for `stream`; `reset` != 0 zeroes the counter afterwards. */
+int ksp_selection_fallback_count(void *stream, unsigned long long *count, int reset);
+
 #ifdef __cplusplus
 }
 #endif

@@ -121,6 +121,7 @@ PROTOTYPES = {
     "ksp_kernel_launch_count": (c_int, [POINTER(ctypes.c_ulonglong)]),
     "ksp_profile_enable": (c_int, [c_int]),
     "ksp_profile_read": (c_int, [POINTER(c_double), POINTER(c_int), c_int]),
+    "ksp_selection_fallback_count": (c_int, [c_void_p, POINTER(ctypes.c_ulonglong), c_int]),
     "ksp_flagger_scratch_bytes": (c_size_t, [POINTER(FlaggerParams)]),
     "ksp_flagger_chunk_baselines": (c_int64, [POINTER(FlaggerParams)]),
     "ksp_flagger": (

@@ -22,6 +22,9 @@ using namespace ksp;
 
 constexpr int SEL_THREADS = 1024;
 
+// rows that fell back to the radix select (diagnostic, see ksp_selection_fallback_count)
+__device__ unsigned long long g_selection_fallbacks;
+
 __device__ __forceinline__ uint32_t mad_key(float v)
 {
     uint32_t b = __float_as_uint(v) & 0x7fffffffu;   // |v|
@@ -78,8 +81,15 @@ __device__ void block_median_keys(const KeySource &key_at, int n, uint32_t n_val
 // If the bracket misses the median (~0.2 % of rows), a private list overflows or the wanted
 // bin is crowded (heavy ties), the row is redone with the 4-pass radix select of select.cuh.
 constexpr int MS_THREADS = 256;
-constexpr int MS_SLOTS = 38;              // list slots per thread (mean use ~16 of 128 keys)
+#ifndef MS_SLOTS_N
+#define MS_SLOTS_N 38
+#endif
+constexpr int MS_SLOTS = MS_SLOTS_N;              // list slots per thread (mean use ~16 of 128 keys)
 constexpr int MS_BINS = 2048;
+#ifndef MS_QLO
+#define MS_QLO 448u                       // bracket = these sample quantiles, in 1/1024
+#define MS_QHI 576u
+#endif
 #ifndef MS_UNROLL
 #define MS_UNROLL 8                       // float4 loads in flight per thread (multiple of 4)
 #endif
@@ -128,6 +138,32 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, int lane)
         if (lane >= d) v += o;
     }
     return v;
+}
+
+// Two-level histogram lookup by one warp: `coarse[j]` = sum of fine[32 j .. 32 j + 31], 64
+// coarse bins.  Finds the fine bin holding rank r (0-based, r < total), the rank inside that
+// bin and the bin's count.  Every lane returns the same values.
+struct BinHit { uint32_t bin, r_in, count; };
+
+__device__ __forceinline__ BinHit locate_rank(const uint32_t *coarse, const uint32_t *fine,
+                                              uint32_t r, uint32_t c0, uint32_t c_excl, int lane)
+{
+    // c0 = coarse[2 lane], c_excl = exclusive prefix of this lane's two coarse bins
+    const uint32_t c1 = coarse[2 * lane + 1];
+    const int src = __ffs(__ballot_sync(0xffffffffu, r >= c_excl && r < c_excl + c0 + c1)) - 1;
+    const uint32_t base = __shfl_sync(0xffffffffu, c_excl, src);
+    const uint32_t first = __shfl_sync(0xffffffffu, c0, src);
+    const bool second = r >= base + first;
+    const uint32_t cbin = 2u * (uint32_t) src + (second ? 1u : 0u);
+    const uint32_t r_c = r - base - (second ? first : 0u);            // rank inside the coarse bin
+    const uint32_t f = fine[cbin * 32u + lane];
+    const uint32_t f_incl = warp_scan_incl(f, lane), f_excl = f_incl - f;
+    const int src2 = __ffs(__ballot_sync(0xffffffffu, r_c >= f_excl && r_c < f_incl)) - 1;
+    BinHit h;
+    h.bin = cbin * 32u + (uint32_t) src2;
+    h.count = __shfl_sync(0xffffffffu, f, src2);
+    h.r_in = r_c - __shfl_sync(0xffffffffu, f_excl, src2);
+    return h;
 }
 
 // One element of the pass, branch-free (7 instructions): three float compares with |x| as an
@@ -187,51 +223,68 @@ madnz_stream_kernel(const float *__restrict__ dev_t, float *__restrict__ noise, 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *row = dev_t + (int64_t) blockIdx.x * stride;
 
-    for (int i = tid; i < MS_BINS; i += MS_THREADS) hist[i] = 0u;
-    if (tid < MS_BINS / 32) coarse[tid] = 0u;
+    if (channels <= 0) {                                      // empty row: no median
+        if (tid == 0) noise[blockIdx.x] = __int_as_float(0x7fc00000);
+        return;
+    }
+    // the sample histogram of step 1 borrows the (still unused) list memory
+    uint32_t *s_fine = lists, *s_coarse = lists + MS_BINS;
+    for (int i = tid; i < MS_BINS; i += MS_THREADS) {
+        hist[i] = 0u;
+        s_fine[i] = 0u;
+    }
+    if (tid < MS_BINS / 32) {
+        coarse[tid] = 0u;
+        s_coarse[tid] = 0u;
+    }
     if (tid < 16) misc[tid] = (tid == 10) ? 0xffffffffu : 0u;
 
-    // ---- 1. bracket: all four sample loads in flight together, then four interleaved sorts;
-    //         every warp reduces the 32 group quantiles itself (no second barrier)
+    // ---- 1. bracket.  1024 samples of the row go into a histogram over the float bit
+    //         patterns (bin = key >> 20: exponent and 3 mantissa bits; coarse = bin >> 5); every
+    //         warp then finds the 44 % and 56 % sample quantiles with two warp scans and
+    //         interpolates linearly inside their bins.  The bracket only has to CONTAIN the
+    //         median - that is verified after the pass - so the estimate need not be exact.
     uint32_t lo, hi;
     {
-        const int step = channels >> 10;
+        const uint32_t step = (uint32_t) channels >> 10;
+        const int last = channels - 1;
         uint32_t key[4];
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-            const int i = tid * 4 + g;                                   // sample number, 0..1023
-            int pos = (int) (((int64_t) i * channels) >> 10);
-            if (step > 1) pos += (int) (((uint32_t) i * 2654435761u) >> 16) % step;
-            key[g] = (channels > 0) ? __float_as_uint(__ldg(row + min(pos, channels - 1))) : 0u;
+            const uint32_t i = (uint32_t) tid * 4u + g;                  // sample number, 0..1023
+            uint32_t pos = (uint32_t) (((uint64_t) i * (uint32_t) channels) >> 10);
+            pos += (((i * 2654435761u) >> 16) * step) >> 16;             // jitter inside the stride
+            key[g] = __float_as_uint(__ldg(row + min((int) pos, last)));
         }
-        int m[4];
-#pragma unroll
-        for (int g = 0; g < 4; g++) {                 // group g = the g-th samples of the warp's lanes
-            const uint32_t k = key[g] & 0x7fffffffu;
-            key[g] = ((k - 1u) < KEY_INF) ? k : 0xffffffffu;
-            m[g] = __popc(__ballot_sync(0xffffffffu, key[g] != 0xffffffffu));
-        }
-        sort32xN<4>(key, lane);
+        __syncthreads();                                                 // histograms are zeroed
 #pragma unroll
         for (int g = 0; g < 4; g++) {
-            const uint32_t lo_g = __shfl_sync(0xffffffffu, key[g], (m[g] * 14) >> 5);
-            const uint32_t hi_g = __shfl_sync(0xffffffffu, key[g],
-                                              min(max(m[g] - 1, 0), (m[g] * 18 + 31) >> 5));
-            if (lane == 0) {
-                misc[64 + warp * 4 + g] = m[g] ? lo_g : 0xffffffffu;
-                misc[96 + warp * 4 + g] = m[g] ? hi_g : 0xffffffffu;
+            const uint32_t k = key[g] & 0x7fffffffu;
+            if ((k - 1u) < KEY_INF) {
+                atomicAdd(&s_fine[k >> 20], 1u);
+                atomicAdd(&s_coarse[k >> 25], 1u);
             }
         }
         __syncthreads();
-        uint32_t q[2] = {misc[64 + lane], misc[96 + lane]};
-        const int cnt_lo = __popc(__ballot_sync(0xffffffffu, q[0] != 0xffffffffu));
-        const int cnt_hi = __popc(__ballot_sync(0xffffffffu, q[1] != 0xffffffffu));
-        sort32xN<2>(q, lane);
-        lo = __shfl_sync(0xffffffffu, q[0], (max(cnt_lo, 1) - 1) >> 1);
-        hi = __shfl_sync(0xffffffffu, q[1], cnt_hi >> 1);
-        if (cnt_lo == 0) lo = 1u;
-        if (cnt_hi == 0) hi = KEY_INF;
-        hi = max(hi, lo);
+        const uint32_t c0 = s_coarse[2 * lane];
+        const uint32_t c01 = c0 + s_coarse[2 * lane + 1];
+        const uint32_t c_incl = warp_scan_incl(c01, lane), c_excl = c_incl - c01;
+        const uint32_t m = __shfl_sync(0xffffffffu, c_incl, 31);          // usable samples
+        lo = 1u;
+        hi = KEY_INF;
+        if (m > 0) {                                                      // block-uniform
+            const uint32_t r_lo = (m * MS_QLO) >> 10;
+            const uint32_t r_hi = min(m - 1u, (m * MS_QHI + 1023u) >> 10);
+            const BinHit a = locate_rank(s_coarse, s_fine, r_lo, c0, c_excl, lane);
+            const BinHit b = locate_rank(s_coarse, s_fine, r_hi, c0, c_excl, lane);
+            const float scale = 1048576.0f;                               // keys per bin
+            lo = (a.bin << 20) + (uint32_t) (__fdividef((float) a.r_in, (float) a.count) * scale);
+            hi = (b.bin << 20) + (uint32_t) (__fdividef((float) (b.r_in + 1u), (float) b.count) * scale);
+            lo = max(lo, 1u);
+            hi = min(hi, KEY_INF);
+            hi = max(hi, lo);
+        }
+        __syncthreads();                              // the lists may now overwrite the sample histogram
     }
     const uint32_t width = hi - lo + 1u;
 
@@ -323,50 +376,42 @@ madnz_stream_kernel(const float *__restrict__ dev_t, float *__restrict__ noise, 
     bool fallback = (misc[2] != 0u) || (r_rel >= kept) || (even && r_rel + 1u >= kept);
 
     if (!fallback) {                                          // block-uniform
-        // coarse level: lane owns coarse bins 2*lane, 2*lane + 1
-        const uint32_t c0 = coarse[2 * lane], c1 = coarse[2 * lane + 1];
-        const uint32_t c_incl = warp_scan_incl(c0 + c1, lane), c_excl = c_incl - (c0 + c1);
-        const int src = __ffs(__ballot_sync(0xffffffffu, r_rel >= c_excl && r_rel < c_incl)) - 1;
-        const uint32_t base = __shfl_sync(0xffffffffu, c_excl, src);
-        const uint32_t first = __shfl_sync(0xffffffffu, c0, src);
-        const bool second = r_rel >= base + first;
-        const uint32_t cbin = 2u * (uint32_t) src + (second ? 1u : 0u);
-        const uint32_t r_c = r_rel - base - (second ? first : 0u);       // rank inside the coarse bin
-        // fine level: lane owns one bin of the coarse bin
-        const uint32_t f = hist[cbin * 32u + lane];
-        const uint32_t f_incl = warp_scan_incl(f, lane), f_excl = f_incl - f;
-        const int src2 = __ffs(__ballot_sync(0xffffffffu, r_c >= f_excl && r_c < f_incl)) - 1;
-        const uint32_t bin = cbin * 32u + (uint32_t) src2;
-        const uint32_t in_bin = __shfl_sync(0xffffffffu, f, src2);
-        const uint32_t r_bin = r_c - __shfl_sync(0xffffffffu, f_excl, src2);   // rank inside the bin
+        const uint32_t c0 = coarse[2 * lane];
+        const uint32_t c01 = c0 + coarse[2 * lane + 1];
+        const uint32_t c_excl = warp_scan_incl(c01, lane) - c01;
+        const BinHit h = locate_rank(coarse, hist, r_rel, c0, c_excl, lane);
         const bool exact_bins = shift == 0;                   // a bin is one key value
-        const bool crowded = !exact_bins && in_bin > (uint32_t) MS_SMALL_CAP;
+        const bool crowded = !exact_bins && h.count > (uint32_t) MS_SMALL_CAP;
+        const bool collect = !exact_bins && !crowded;
 
-        // second walk over the lists: the keys of the wanted bin, and the smallest key beyond it
-        uint32_t above = 0xffffffffu;
+        // second walk over the lists: the keys of the wanted bin, and the smallest key beyond
+        // it.  d = key - first key of the bin; keys beyond the bin have d >= span, and
+        // d - span wraps to >= 2^31 for all others.
+        const uint32_t bin_first = lo + (h.bin << shift), span = 1u << shift;
+        uint32_t beyond = 0xffffffffu;
         for (uint32_t k = 0; k < n_mine; k++) {
             const uint32_t key = mine[k * MS_THREADS] & 0x7fffffffu;
-            const uint32_t b = (key - lo) >> shift;
-            if (b == bin && !exact_bins && !crowded) misc[128 + atomicAdd(&misc[8], 1u)] = key;
-            above = min(above, b > bin ? key : 0xffffffffu);
+            const uint32_t d = key - bin_first;
+            if (d < span && collect) misc[128 + atomicAdd(&misc[8], 1u)] = key;
+            beyond = min(beyond, d - span);
         }
-        above = __reduce_min_sync(0xffffffffu, above);
-        if (lane == 0 && above != 0xffffffffu) atomicMin(&misc[10], above);
+        beyond = __reduce_min_sync(0xffffffffu, beyond);
+        if (lane == 0 && beyond < 0x80000000u) atomicMin(&misc[10], beyond);
         __syncthreads();
         if (crowded) {
             fallback = true;                                  // heavy ties: block-uniform
         } else {
             if (warp == 0) {
-                uint32_t v1, nxt;                             // rank r_bin and r_bin + 1 inside the bin
+                uint32_t v1, nxt;                             // ranks r_in and r_in + 1 inside the bin
                 if (exact_bins) {
-                    v1 = lo + bin;
+                    v1 = bin_first;
                     nxt = v1;
                 } else {
-                    const uint32_t srt = sort32(lane < (int) in_bin ? misc[128 + lane] : 0xffffffffu, lane);
-                    v1 = __shfl_sync(0xffffffffu, srt, (int) r_bin);
-                    nxt = __shfl_sync(0xffffffffu, srt, (int) min(r_bin + 1u, 31u));
+                    const uint32_t srt = sort32(lane < (int) h.count ? misc[128 + lane] : 0xffffffffu, lane);
+                    v1 = __shfl_sync(0xffffffffu, srt, (int) h.r_in);
+                    nxt = __shfl_sync(0xffffffffu, srt, (int) min(h.r_in + 1u, 31u));
                 }
-                const uint32_t v2 = !even ? v1 : (r_bin + 1u < in_bin ? nxt : misc[10]);
+                const uint32_t v2 = !even ? v1 : (h.r_in + 1u < h.count ? nxt : bin_first + span + misc[10]);
                 if (lane == 0) noise[blockIdx.x] = mad_finish(v1, v2);
             }
             return;
@@ -381,7 +426,10 @@ madnz_stream_kernel(const float *__restrict__ dev_t, float *__restrict__ noise, 
         sc.misc = misc + 16;
         auto src = [row](int i) { return mad_key(row[i]); };
         block_median_keys<MS_THREADS>(src, channels, n_valid, sc, v1, v2);
-        if (tid == 0) noise[blockIdx.x] = mad_finish(v1, v2);
+        if (tid == 0) {
+            noise[blockIdx.x] = mad_finish(v1, v2);
+            atomicAdd(&g_selection_fallbacks, 1ull);
+        }
     }
 }
 
@@ -784,6 +832,7 @@ percentile5_stream_kernel(const void *__restrict__ src, float *__restrict__ dest
         sc.misc = misc + 16;
         auto key_at = [src, off](int i) { return p5_key<MODE>(src, off + i); };
         found[k] = block_radix_select<P5_THREADS>(key_at, n, ranks[k], sc);
+        if (tid == 0) atomicAdd(&g_selection_fallbacks, 1ull);
     }
     if (tid == 0) {
         const int64_t r = blockIdx.x;
@@ -803,6 +852,18 @@ size_t select_smem_bytes(int64_t n, bool in_smem)
 }
 
 }  // namespace
+
+extern "C" int ksp_selection_fallback_count(void *stream, unsigned long long *count, int reset)
+{
+    if (!count) return KSP_EINVAL;
+    KSP_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+    KSP_CUDA(cudaMemcpyFromSymbol(count, g_selection_fallbacks, sizeof(*count)));
+    if (reset) {
+        const unsigned long long zero = 0;
+        KSP_CUDA(cudaMemcpyToSymbol(g_selection_fallbacks, &zero, sizeof(zero)));
+    }
+    return 0;
+}
 
 extern "C" int ksp_madnz_t(void *stream, const float *dev_t, float *noise, int64_t channels,
                            int64_t baselines, int64_t stride)

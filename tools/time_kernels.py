@@ -80,6 +80,11 @@ def main():
             "ksp_transpose", S, p(dev_t), p(dev_cm), C, B, CT, B, 4), args.reps, flush), 8)
         rec("madnz_t", timeit(lambda: _capi.call(
             "ksp_madnz_t", S, p(dev_t), p(noise), C, B, CT), args.reps, flush), 4)
+        fb = ctypes.c_ulonglong(0)
+        _capi.call("ksp_selection_fallback_count", S, byref(fb), 1)
+        _capi.call("ksp_madnz_t", S, p(dev_t), p(noise), C, B, CT)
+        _capi.call("ksp_selection_fallback_count", S, byref(fb), 1)
+        print("madnz_t fallback rows", fb.value, "of", B, flush=True)
         rec("madnz", timeit(lambda: _capi.call(
             "ksp_madnz", S, p(dev_cm), p(noise), C, B, B), args.reps, flush), 4)
         rec("threshold_sum7", timeit(lambda: _capi.call(
