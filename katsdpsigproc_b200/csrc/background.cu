@@ -233,6 +233,72 @@ __device__ __forceinline__ bool tile_phase1(const BgArgs &a, int64_t b0, int c0,
     return any_bad;
 }
 
+// Interior tiles without flags, complex input: the same work with the loads software-pipelined
+// BG_PF groups ahead in registers, so that every thread keeps loads in flight while it does the
+// amplitude arithmetic of an earlier group (phase 1 is otherwise latency-bound: issue 8 loads,
+// wait, compute, repeat).
+#ifndef BG_PF
+#define BG_PF 3
+#endif
+template <int IN_MODE, int TC>
+__device__ __forceinline__ bool tile_phase1_pipelined(const BgArgs &a, int64_t b0, int c0, float *amp_sm)
+{
+    using G = TileGeom<TC>;
+    constexpr int NWARPS = BG_THREADS / 32;
+    constexpr int NEEDED = (TC + HALO_L + 6 + 3) / 4;    // groups that phase 2 reads
+    constexpr int MAX_IT = (NEEDED + NWARPS - 1) / NWARPS;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int64_t b = min(b0 + lane, a.baselines - 1);
+    const int64_t row_bytes = a.vis_stride * 8;
+    const int n_it = (NEEDED - warp + NWARPS - 1) / NWARPS;          // groups warp, warp + 8, ...
+    const char *p = reinterpret_cast<const char *>(a.vis) +
+                    ((int64_t) (c0 - HALO_L + 4 * warp) * a.vis_stride + b) * 8;
+    const int64_t group_bytes = 4 * NWARPS * row_bytes;
+    float *dst = amp_sm + lane * G::P + 4 * warp;
+    float2 buf[BG_PF + 1][4];
+    auto load = [&](float2 (&r)[4], const char *q) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            r[k] = ldg_stream_f2(reinterpret_cast<const float2 *>(q));
+            q += row_bytes;
+        }
+    };
+#pragma unroll
+    for (int d = 0; d < BG_PF; d++) {
+        if (d < n_it) load(buf[d], p);
+        p += group_bytes;
+    }
+    bool any_bad = false;
+#pragma unroll
+    for (int it = 0; it < MAX_IT; it++) {
+        if (it < n_it) {
+            if (it + BG_PF < n_it) load(buf[(it + BG_PF) % (BG_PF + 1)], p);
+            p += group_bytes;
+            const float2 (&r)[4] = buf[it % (BG_PF + 1)];
+            float v[4];
+            unsigned redo = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                bool ok;
+                v[k] = abs_numpy_try(r[k].x, r[k].y, ok);
+                redo |= (ok ? 0u : 1u) << k;
+            }
+            if (redo) {
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if ((redo >> k) & 1u)
+                        v[k] = abs_slow_call(r[k].x, r[k].y, IN_MODE == IN_NUMPY ? KSP_ABS_NUMPY : KSP_ABS_HYPOT);
+            }
+            const float probe = (v[0] + v[1]) + (v[2] + v[3]);
+            any_bad |= (probe != probe);
+            *reinterpret_cast<float4 *>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+            dst += 4 * NWARPS;
+        }
+    }
+    return any_bad;
+}
+
 template <int IN_MODE, int FLAG_MODE, bool TRANSPOSED, int TC>
 __global__ void __launch_bounds__(BG_THREADS, BG_MIN_BLOCKS)
 bg13_kernel(const BgArgs a)
@@ -249,7 +315,9 @@ bg13_kernel(const BgArgs a)
     {
         const bool interior = (c0 - HALO_L >= 0) && (c0 + TC + HALO_R <= C);   // block-uniform
         bool any_bad;
-        if (interior)
+        if (interior && IN_MODE == IN_NUMPY && FLAG_MODE == KSP_FLAGS_NONE && BG_PF > 0)
+            any_bad = tile_phase1_pipelined<IN_MODE, TC>(a, b0, c0, amp_sm);
+        else if (interior)
             any_bad = tile_phase1<IN_MODE, FLAG_MODE, true, TC>(a, b0, c0, amp_sm);
         else
             any_bad = tile_phase1<IN_MODE, FLAG_MODE, false, TC>(a, b0, c0, amp_sm);

@@ -15,11 +15,12 @@ Nothing here is specific to one GPU: with baseline sharding each rank owns one
 
 from __future__ import annotations
 
+import asyncio
 from typing import Any, List, Mapping, Optional
 
 import numpy as np
 
-from . import accel
+from . import accel, resource
 from .rfi import device as rfi_device
 
 
@@ -119,6 +120,15 @@ class StreamingFlagger:
         elif input_flags is not None:
             raise TypeError("input flags were provided but not included in the template")
 
+        self._enqueue(slot)
+        slot.busy = True
+        self._pending.append(slot)
+        self._next = (self._next + 1) % len(self._slots)
+        return result
+
+    def _enqueue(self, slot: _Slot) -> None:
+        """Upload, flag and download the dump staged in ``slot``'s pinned arrays: three queues,
+        ordered by events, nothing blocks."""
         # upload: the device vis buffer is free once the previous flagging of this slot is done
         if slot.computed is not None:
             self.upload_queue.enqueue_wait_for_events([slot.computed])
@@ -139,10 +149,6 @@ class StreamingFlagger:
         slot.host_flags = slot.host_flags_pair[slot.uses & 1]
         slot.flags.get_async(self.download_queue, slot.host_flags)
         slot.downloaded = self.download_queue.enqueue_marker()
-        slot.busy = True
-        self._pending.append(slot)
-        self._next = (self._next + 1) % len(self._slots)
-        return result
 
     def _collect(self, slot: _Slot) -> np.ndarray:
         assert self._pending and self._pending[0] is slot
@@ -157,3 +163,73 @@ class StreamingFlagger:
         while self._pending:
             out.append(self._collect(self._pending[0]))
         return out
+
+
+class AsyncStreamingFlagger:
+    """The same pipeline for asyncio applications, built from the reference's own ordering
+    primitives (:class:`~katsdpsigproc_b200.resource.Resource`, ``async_wait_for_events``;
+    the pattern of the reference's ``doc/user/resource.rst``).
+
+    Every buffer set is a :class:`Resource`; :meth:`submit` takes the next one in round-robin
+    order and returns a task that resolves to the flags of that dump.  Tasks complete in
+    submission order per buffer set, and the event loop is never blocked: host-side waits
+    and the staging copy run in the default executor.
+
+    ::
+
+        stream = AsyncStreamingFlagger(template, channels, baselines, threshold_args={...})
+        jobs = resource.JobQueue()
+        async for vis in receiver:
+            jobs.add(consume(stream.submit(vis)))
+            await jobs.finish(max_remaining=stream.depth - 1)
+        await jobs.finish()
+
+    The array a task returns is a pinned buffer owned by the object; it stays valid until
+    ``depth`` further dumps have been submitted AND awaited.
+    """
+
+    def __init__(self, template: rfi_device.FlaggerDeviceTemplate, channels: int, baselines: int,
+                 depth: int = 2, background_args: Mapping[str, Any] = {},
+                 noise_est_args: Mapping[str, Any] = {}, threshold_args: Mapping[str, Any] = {},
+                 loop: Optional[asyncio.AbstractEventLoop] = None) -> None:
+        self._engine = StreamingFlagger(template, channels, baselines, depth, background_args,
+                                        noise_est_args, threshold_args)
+        if loop is None:
+            loop = asyncio.get_event_loop()
+        self._loop = loop
+        self._resources = [resource.Resource(slot, loop=loop) for slot in self._engine._slots]
+        self._next = 0
+
+    @property
+    def depth(self) -> int:
+        return len(self._resources)
+
+    def submit(self, vis: np.ndarray, input_flags: Optional[np.ndarray] = None
+               ) -> "asyncio.Future[np.ndarray]":
+        """Queue one dump; returns a task whose result is the ``uint8`` flag array."""
+        alloc = self._resources[self._next].acquire()      # order is fixed here, synchronously
+        self._next = (self._next + 1) % len(self._resources)
+        return asyncio.ensure_future(self._run(alloc, vis, input_flags), loop=self._loop)
+
+    async def _run(self, alloc: "resource.ResourceAllocation[_Slot]", vis: np.ndarray,
+                   input_flags: Optional[np.ndarray]) -> np.ndarray:
+        with alloc as slot:
+            await alloc.wait_events()                       # earlier dump in this buffer set is out
+            if (slot.input_flags is None) != (input_flags is None):
+                alloc.ready()
+                raise TypeError("input flags were provided but not included in the template"
+                                if input_flags is not None else
+                                "input flags were expected but not provided")
+
+            def stage() -> None:
+                np.copyto(slot.host_vis, vis, casting="no")
+                if input_flags is not None:
+                    np.copyto(slot.host_input_flags, input_flags, casting="no")
+            await self._loop.run_in_executor(None, stage)
+            with self._engine.context:
+                self._engine._enqueue(slot)
+            flags = slot.host_flags
+            downloaded = slot.downloaded
+            await resource.async_wait_for_events([downloaded], loop=self._loop)
+            alloc.ready()                                   # everything of this dump has left the device
+            return flags

@@ -360,6 +360,53 @@ def test_streaming_flagger(context, abs_mode, depth, use_flags):
         stream.submit(dumps[0], None if use_flags else np.zeros(channels, np.uint8))
 
 
+@pytest.mark.parametrize("depth", [1, 3])
+def test_async_streaming_flagger(context, abs_mode, depth):
+    """The asyncio pipeline (Resource / JobQueue / async_wait_for_events): results arrive in
+    submission order and equal the oracle while the producer keeps `depth` dumps in flight."""
+    import asyncio
+
+    from katsdpsigproc_b200 import resource, streaming
+
+    channels, baselines = 384, 45
+    template = rfi.FlaggerDeviceTemplate(
+        rfi.BackgroundMedianFilterDeviceTemplate(context, 13, abs_mode=abs_mode),
+        rfi.NoiseEstMADTDeviceTemplate(context, 10240),
+        rfi.ThresholdSumDeviceTemplate(context, n_windows=5))
+    rs = np.random.RandomState(11)
+    dumps = []
+    for i in range(6):
+        vis = complex_normal(rs, (channels, baselines))
+        vis += ((rs.random_sample(vis.shape) < 1 / 32) * 60.0).astype(np.complex64)
+        dumps.append(vis)
+
+    async def main():
+        stream = streaming.AsyncStreamingFlagger(template, channels, baselines, depth=depth,
+                                                 threshold_args={"n_sigma": 9.0})
+        assert stream.depth == depth
+        jobs = resource.JobQueue()
+        results = []
+
+        async def consume(task):
+            results.append((await task).copy())
+        for vis in dumps:
+            jobs.add(consume(stream.submit(vis)))
+            await jobs.finish(max_remaining=depth - 1)
+        await jobs.finish()
+        with pytest.raises(TypeError):
+            await stream.submit(dumps[0], np.zeros(channels, np.uint8))
+        # the failed submission released its buffer set: the stream still works
+        again = (await stream.submit(dumps[0])).copy()
+        return results, again
+
+    results, again = asyncio.run(main())
+    assert len(results) == len(dumps)
+    for vis, got in zip(dumps, results):
+        want, _, _ = contract.flagger(vis, None, n_windows=5, n_sigma=9.0, abs_mode=abs_mode)
+        np.testing.assert_array_equal(want, got)
+    np.testing.assert_array_equal(results[0], again)
+
+
 def test_wrap_external_device_memory(context, command_queue, abs_mode):
     """Zero-copy hand-over: bind a torch tensor's memory as the flagger's vis buffer."""
     torch = pytest.importorskip("torch")
