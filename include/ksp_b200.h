@@ -36,6 +36,8 @@ extern "C" {
 #define KSP_EALIGN (-2)      /* pointer or stride not aligned as documented */
 #define KSP_ETOOLARGE (-3)   /* exceeds a documented limit (channels, width, windows) */
 #define KSP_ESCRATCH (-4)    /* scratch buffer too small */
+#define KSP_ENOJIT (-5)      /* the run-time compiler (NVRTC) is not available */
+#define KSP_EJIT (-6)        /* run-time compilation failed: see ksp_jit_log() */
 
 /* complex64 amplitude rule: which host np.abs the result equals */
 #define KSP_ABS_NUMPY 0      /* numpy on AVX-512F hosts: L*sqrt(fma(r,r,1)), r = min/max */
@@ -194,6 +196,28 @@ int64_t ksp_flagger_chunk_baselines(const ksp_flagger_params *p);
 int ksp_flagger(void *stream, const ksp_flagger_params *p, const void *vis,
                 const uint8_t *input_flags, float *noise, uint8_t *flags, void *scratch,
                 size_t scratch_bytes);
+
+/* ------------------------------------------------------------------------
+ * General-purpose operations that sit beside the RFI ones in the reference.
+ * ---------------------------------------------------------------------- */
+/* Fill.  Replaces fill.mako (reference fill.py:130-139): data[i] = *value for
+ * i < elements, where an element is elem_size (1, 2, 4, 8 or 16) opaque bytes. */
+int ksp_fill(void *stream, void *data, size_t elements, const void *value, size_t elem_size);
+
+/* HReduce.  Replaces hreduce.mako (reference reduce.py:72-89, 199-214): for every row,
+ * dest[row] = op-reduction of src[row, first_col .. first_col + n_cols).  As in the
+ * reference the element type and the combining step are C source text (`ctype`, e.g.
+ * "unsigned int"; `op`, an expression in a and b, e.g. "a + b"; `identity`, e.g. "0";
+ * optional `extra_code` pasted in front), compiled when the template is created - here with
+ * NVRTC for sm_100a, loaded lazily with dlopen.  KSP_ENOJIT if NVRTC cannot be loaded,
+ * KSP_EJIT if the text does not compile (ksp_jit_log() returns the compiler output of the
+ * calling thread's last ksp_hreduce_create).  op must be commutative and associative. */
+int ksp_hreduce_create(const char *ctype, const char *op, const char *identity,
+                       const char *extra_code, size_t elem_size, void **handle);
+int ksp_hreduce(void *stream, void *handle, const void *src, void *dest, int64_t rows,
+                int64_t src_stride, int64_t first_col, int64_t n_cols);
+int ksp_hreduce_destroy(void *handle);
+const char *ksp_jit_log(void);
 
 /* ------------------------------------------------------------------------
  * Introspection (no reference equivalent; used by bench.py and the tests).

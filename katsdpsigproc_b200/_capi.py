@@ -118,6 +118,14 @@ PROTOTYPES = {
     ),
     "ksp_maskedsum": (
         c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int, c_int]),
+    "ksp_fill": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t]),
+    "ksp_hreduce_create": (
+        c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_size_t,
+                POINTER(c_void_p)]),
+    "ksp_hreduce": (
+        c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64]),
+    "ksp_hreduce_destroy": (c_int, [c_void_p]),
+    "ksp_jit_log": (ctypes.c_char_p, []),
     "ksp_kernel_launch_count": (c_int, [POINTER(ctypes.c_ulonglong)]),
     "ksp_profile_enable": (c_int, [c_int]),
     "ksp_profile_read": (c_int, [POINTER(c_double), POINTER(c_int), c_int]),

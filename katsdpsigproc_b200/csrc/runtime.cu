@@ -16,6 +16,8 @@ const char *ksp_error_string(int code)
     case KSP_EALIGN: return "pointer or stride is not aligned as the C ABI requires";
     case KSP_ETOOLARGE: return "argument exceeds a documented limit";
     case KSP_ESCRATCH: return "scratch buffer too small";
+    case KSP_ENOJIT: return "run-time compiler (NVRTC) not available";
+    case KSP_EJIT: return "run-time compilation failed (see ksp_jit_log)";
     default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t) code);

@@ -423,3 +423,120 @@ def test_wrap_external_device_memory(context, command_queue, abs_mode):
     wrapped = DeviceArray.wrap(context, t.data_ptr(), (256, 64), np.complex64, owner=t)
     fn(vis=wrapped)
     np.testing.assert_array_equal(spikes.astype(np.uint8), fn.buffer("flags").get(command_queue))
+
+
+# ----------------------------------------------------------------------------- Fill / HReduce
+@pytest.mark.parametrize("dtype, ctype, value", [
+    (np.uint8, "unsigned char", 0xA5),
+    (np.int16, "short", -1234),
+    (np.float32, "float", 1.5e-3),
+    (np.uint32, "unsigned int", 0xDEADBEEF),
+    (np.complex64, "float2", 2.5 - 1.25j),
+    (np.complex128, "double2", -3.0 + 7.0j),
+])
+@pytest.mark.parametrize("shape", [(75, 63), (1,), (1000003,)])
+def test_fill(context, command_queue, dtype, ctype, value, shape):
+    """Reference test/test_fill.py:35-56: every element INCLUDING the padding takes the value."""
+    from katsdpsigproc_b200 import fill
+
+    template = fill.FillTemplate(context, dtype, ctype)
+    fn = template.instantiate(command_queue, shape)
+    for dim, extra in zip(fn.slots["data"].dimensions, (5, 10)):
+        accel.Dimension(dim.size, min_padded_size=dim.size + extra).link(dim)
+    fn.ensure_all_bound()
+    data = fn.buffer("data")
+    assert all(p >= s + 5 for p, s in zip(data.padded_shape, shape))
+    poison = data.empty_like()                  # so that untouched bytes are noticed
+    HostArray.padded_view(poison).view(np.uint8)[...] = 0x3C
+    data.set(command_queue, poison)
+    fn.set_value(value)
+    fn()
+    ret = data.get(command_queue)
+    want = np.dtype(dtype).type(value)
+    whole = HostArray.padded_view(ret)
+    assert whole.shape == data.padded_shape
+    assert np.all(whole == want)
+    assert fn.parameters()["value"] == want
+    # the default value is the dtype's zero
+    assert template.instantiate(command_queue, shape).value == np.dtype(dtype).type()
+    fn.set_value(0)
+    fn()
+    assert not np.any(HostArray.padded_view(data.get(command_queue)).view(np.uint8))
+
+
+@pytest.mark.parametrize("rows, columns, column_range", [
+    (129, 173, (67, 128)),
+    (7, 8, (1, 7)),            # narrower than a warp
+    (64, 5000, None),
+    (1, 1, None),
+])
+def test_hreduce_sum_uint32(context, command_queue, rows, columns, column_range):
+    """Reference test/test_reduce.py:86-107 (uint32 'a + b', identity '0') plus wider shapes."""
+    from katsdpsigproc_b200 import reduce
+
+    template = reduce.HReduceTemplate(context, np.uint32, "unsigned int", "a + b", "0")
+    fn = template.instantiate(command_queue, (rows, columns), column_range)
+    fn.ensure_all_bound()
+    src = fn.buffer("src").empty_like()
+    rs = np.random.RandomState(1)
+    src[:] = rs.randint(0, 100000, (rows, columns))
+    fn.buffer("src").set(command_queue, src)
+    fn()
+    dest = fn.buffer("dest").get(command_queue)
+    lo, hi = column_range if column_range else (0, columns)
+    np.testing.assert_equal(np.sum(src[:, lo:hi], axis=1, dtype=np.uint32), dest)
+    assert fn.parameters()["column_range"] == (lo, hi)
+
+
+def test_hreduce_other_operators(context, command_queue):
+    from katsdpsigproc_b200 import reduce
+
+    rs = np.random.RandomState(2)
+    rows, columns = 37, 1234
+    data = rs.standard_normal((rows, columns)).astype(np.float32)
+    # max of floats
+    t = reduce.HReduceTemplate(context, np.float32, "float", "fmaxf(a, b)", "-INFINITY")
+    fn = t.instantiate(command_queue, (rows, columns), (3, 1200))
+    fn.ensure_all_bound()
+    fn.buffer("src").set(command_queue, data)
+    fn()
+    np.testing.assert_array_equal(data[:, 3:1200].max(axis=1), fn.buffer("dest").get(command_queue))
+    # a two-field element with helper code: (min, max) pairs, 8 bytes per element
+    pairs = np.stack([data, data], axis=-1).copy().view(np.complex64)[..., 0]
+    extra = ("struct mm { float lo, hi; };\n"
+             "__device__ mm mm_join(mm a, mm b) { mm r; r.lo = fminf(a.lo, b.lo); "
+             "r.hi = fmaxf(a.hi, b.hi); return r; }\n"
+             "__device__ mm mm_id() { mm r; r.lo = INFINITY; r.hi = -INFINITY; return r; }\n")
+    t2 = reduce.HReduceTemplate(context, np.complex64, "mm", "mm_join(a, b)", "mm_id()", extra)
+    fn2 = t2.instantiate(command_queue, (rows, columns))
+    fn2.ensure_all_bound()
+    fn2.buffer("src").set(command_queue, pairs)
+    fn2()
+    out = fn2.buffer("dest").get(command_queue)
+    np.testing.assert_array_equal(data.min(axis=1), out.real)
+    np.testing.assert_array_equal(data.max(axis=1), out.imag)
+    # float64 sum: tree order differs from numpy's, compare to rounding error
+    d64 = rs.standard_normal((rows, columns))
+    t3 = reduce.HReduceTemplate(context, np.float64, "double", "a + b", "0.0")
+    fn3 = t3.instantiate(command_queue, (rows, columns))
+    fn3.ensure_all_bound()
+    fn3.buffer("src").set(command_queue, d64)
+    fn3()
+    np.testing.assert_allclose(d64.sum(axis=1), fn3.buffer("dest").get(command_queue),
+                               rtol=0, atol=1e-11)
+
+
+def test_hreduce_errors(context, command_queue):
+    from katsdpsigproc_b200 import reduce
+
+    with pytest.raises(RuntimeError, match="could not be built"):
+        reduce.HReduceTemplate(context, np.float32, "float", "a +* b", "0")
+    with pytest.raises(RuntimeError, match="sizes differ"):
+        reduce.HReduceTemplate(context, np.float32, "double", "a + b", "0")
+    t = reduce.HReduceTemplate(context, np.int32, "int", "a + b", "0")
+    with pytest.raises(ValueError):
+        t.instantiate(command_queue, (4, 5, 6))
+    with pytest.raises(ValueError):
+        t.instantiate(command_queue, (4, 5), (0, 6))
+    with pytest.raises(ValueError):
+        t.instantiate(command_queue, (4, 5), (3, 3))
