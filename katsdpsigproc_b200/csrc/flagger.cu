@@ -68,8 +68,8 @@ Layout make_layout(const ksp_flagger_params *p)
     // Chunks in flight ("lanes", KSP_LANES, default 4): consecutive chunks run on separate
     // internal streams so that the tail of one kernel overlaps the next chunk's kernels.
     // Measured on B200 (profiles/): the stages are issue-bound rather than HBM-bound and launches
-    // cost ~9 us each, so few large chunks beat many L2-sized ones; the default is one chunk per
-    // lane, at most 32 baselines per SM each (KSP_CHUNK / chunk_baselines override).
+    // cost ~9 us each, so few large chunks beat many L2-sized ones (KSP_CHUNK / chunk_baselines
+    // override the default below).
     const char *e = getenv("KSP_LANES");
     int lanes = e ? atoi(e) : 4;
     if (lanes < 1) lanes = 1;
@@ -79,9 +79,18 @@ Layout make_layout(const ksp_flagger_params *p)
         const char *c = getenv("KSP_CHUNK");
         chunk = c ? atoll(c) : 0;
         if (chunk <= 0) {
-            chunk = ksp_divup(ksp_divup(p->baselines, lanes), 32) * 32;
-            const int64_t cap = 32 * (int64_t) ksp_sm_count();
-            if (chunk > cap) chunk = cap;
+            // Whole waves: with 16 baselines per SM a chunk is exactly 16 waves of the
+            // background kernel (4 blocks of 32 baselines x 256 channels per SM, 32768 channels)
+            // and 4 waves of the noise kernel (4 one-row blocks per SM), so no launch ends on a
+            // nearly empty wave.  Take the multiple of that unit nearest to an even split over
+            // the lanes; shards smaller than one unit are split evenly instead.
+            const int64_t unit = 16 * (int64_t) ksp_sm_count();
+            if (p->baselines >= unit) {
+                int64_t k = (p->baselines + (int64_t) lanes * unit / 2) / ((int64_t) lanes * unit);
+                chunk = unit * (k < 1 ? 1 : k);
+            } else {
+                chunk = ksp_divup(ksp_divup(p->baselines, lanes), 32) * 32;
+            }
         }
     }
     chunk = (chunk / 32) * 32;

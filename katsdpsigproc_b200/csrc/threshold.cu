@@ -342,15 +342,32 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
     };
 
     // Almost always no thread of the block has anything left to look at: one vote then
-    // replaces the whole window-size loop (and its barrier per size).
+    // replaces the whole window-size loop (and its barrier per size).  The vote uses a cheaper,
+    // slightly more conservative form of hot_starts: sizes 2..8 share the strictest of their
+    // limits (one comparison against the largest sample within reach), sizes 16..64 keep the
+    // positive-sum bound, and band edges are ignored (a false "maybe" only costs the loop).
     {
+        float lim_small = __int_as_float(0x7f800000);          // strictest limit of the sizes <= 8
         bool any = false;
+        const int nf1 = __popc(F) + __popc(F1), nf2 = nf1 + __popc(F2);
+        const float bound1 = ppos + st1.y, bound2 = bound1 + st2.y;
         for (int w = 1; w < a.n_windows; w++) {
-            if ((1 << w) > C) break;
+            const int win = 1 << w;
+            if (win > C) break;
             const float tw = thr[w];
             if (tw != tw) continue;
-            any |= hot_starts(w, tw) != 0u;
+            if (!(tw >= 0.0f)) {
+                any = true;                                    // negative threshold: everything is hot
+            } else if (win <= 8) {
+                lim_small = fminf(lim_small, __fmul_rd(tw, 0.99999905f));
+            } else {
+                const bool two = win > RUN;
+                const float t_min = tw * (float) max(win - (two ? nf2 : nf1), 0);
+                any |= !((two ? bound2 : bound1) <= __fmul_rd(t_min, 0.99999f));
+            }
         }
+        const float reach_max = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), st1.x);
+        any |= !(reach_max <= lim_small);
         if (!__syncthreads_or(any)) goto write_out;
     }
 
