@@ -15,13 +15,16 @@
 // Almost no window ever fires, so the kernel does not build the trees.  It FILTERS with
 // cheap window sums and evaluates the tree only for the survivors:
 //
-//   * mapping: one thread per run of 32 consecutive channels, one block per span of
-//     T * 32 channels of one baseline (spans overlap by the reach of the largest window,
-//     128 channels, so blocks are independent and small: several per SM);
-//   * staging: ONE TMA tile load per block (cp.async.bulk.tensor over dev_t viewed as
+//   * mapping: one thread per run of 32 consecutive channels, one tile = a span of T * 32
+//     channels of one baseline (spans overlap by the reach of the largest window, 128
+//     channels, so tiles are independent); a persistent grid (4 blocks of 128 threads per SM)
+//     walks the tiles;
+//   * staging: ONE TMA tile load per tile (cp.async.bulk.tensor over dev_t viewed as
 //     [baseline][run][32 floats], 128-byte swizzle, hardware zero fill outside the band,
-//     completion on an mbarrier) puts the span in shared memory; plain vector loads into the
-//     same layout when the shape does not allow a tensor map;
+//     completion on an mbarrier) puts the span in shared memory, double-buffered: the load of
+//     a block's next tile is issued before it starts on the current one, so the memory system
+//     always has 2 x 16 KB per block in flight (the kernel was latency-bound without it);
+//     plain vector loads into the same layout when the shape does not allow a tensor map;
 //   * every thread publishes its 32 flags and three statistics of its run (maximum of the
 //     first 8 samples, sum of the positive samples, sum of |u|) in shared memory;
 //   * window size 2^w, thread by thread, cheapest test first:
@@ -67,6 +70,8 @@ struct TsArgs {
     int n_windows;
     int flag_value;
     int use_tma;           // stage the span with one TMA tile load (needs tmap)
+    int two_buffers;       // with TMA: second span buffer, the next tile loads while this one is worked on
+    int n_chunks;          // spans per row
     int chunk_valid;       // channels produced per block (multiple of 32)
     int edge;              // halo on each side of a span (multiple of 32; 0 when one block per row)
     double n_sigma;
@@ -177,8 +182,11 @@ __device__ __noinline__ uint32_t window_candidates(const float *rowbuf, int r, u
 
 // TFIX: block size known at compile time (0 = use blockDim.x); lets the staging loop use
 // immediate offsets.
+#ifndef TS_MIN_BLOCKS
+#define TS_MIN_BLOCKS 4
+#endif
 template <bool PACKED, int TFIX>
-__global__ void __launch_bounds__(TFIX ? TFIX : TS_MAX_THREADS, TFIX ? 6 : 4)
+__global__ void __launch_bounds__(TFIX ? TFIX : TS_MAX_THREADS, TFIX ? TS_MIN_BLOCKS : 4)
 threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(1024) uint8_t sm_raw[];
@@ -189,38 +197,82 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
     const int span = T * RUN;
     const float neg_inf = -__int_as_float(0x7f800000);
 
-    float *rowbuf = sm;                                        // (T + 2) * PITCH: the staged samples x
-    float4 *stat = reinterpret_cast<float4 *>(rowbuf + (T + 2) * PITCH);    // T + 2: run statistics
+    // two span buffers of (T + 2) * PITCH floats (the second only with two_buffers), then the
+    // per-run state
+    float *rowbuf0 = sm;
+    float *rowbuf1 = rowbuf0 + (a.two_buffers ? (T + 2) * PITCH : 0);
+    float4 *stat = reinterpret_cast<float4 *>(rowbuf1 + (T + 2) * PITCH);   // T + 2: run statistics
     uint32_t *Fsm = reinterpret_cast<uint32_t *>(stat + T + 2);             // T + 2
     uint32_t *car1 = Fsm + T + 2;                              // T
     uint32_t *car2 = car1 + T;                                 // T
     float *thr = reinterpret_cast<float *>(car2 + T);          // TS_MAX_WINDOWS (+1)
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(thr + 8);    // TMA completion barrier
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(thr + 8);    // TMA completion barriers, one per buffer
 
-    const int64_t row = blockIdx.x;
     const int C = (int) a.channels;
-    const int base = (int) blockIdx.y * a.chunk_valid - a.edge;     // row channel of slot 0
-    const float *src = a.dev_t + row * a.dev_stride;
+    const int64_t total = a.baselines * (int64_t) a.n_chunks;  // tiles = (row, span) pairs
 
-    if (tid < a.n_windows)
-        thr[tid] = __double2float_rn((a.n_sigma * (double) a.noise[row]) * a.scales[tid]);
+    // ---- once per block
     if (tid < 2) {
         Fsm[T + tid] = 0u;
         stat[T + tid] = make_float4(neg_inf, 0.0f, 0.0f, 0.0f);
     }
-    for (int i = tid; i < 2 * PITCH; i += T) rowbuf[T * PITCH + i] = 0.0f;   // two runs of zeros past the span
+    for (int i = tid; i < 2 * PITCH; i += T) {                 // two runs of zeros past each span
+        rowbuf0[T * PITCH + i] = 0.0f;
+        rowbuf1[T * PITCH + i] = 0.0f;
+    }
+    if (a.use_tma && tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+    }
+    __syncthreads();
+    // one TMA tile load stages a span: T runs of 128 bytes, swizzled, out-of-band runs zero-filled
+    // by the hardware, completion on the buffer's mbarrier
+    auto issue_tile = [&](int64_t r, int y, int buf) {
+        mbar_expect_tx(&mbar[buf], (uint32_t) span * 4u);
+        tma_load_3d(buf ? rowbuf1 : rowbuf0, &tmap, 0, (y * a.chunk_valid - a.edge) >> 5, (int) r, &mbar[buf]);
+    };
+    // tile -> (row, span) without a division per tile: step both by the grid size
+    int64_t row = (int64_t) blockIdx.x / a.n_chunks;
+    int span_y = (int) ((int64_t) blockIdx.x - row * a.n_chunks);
+    const int64_t step_rows = (int64_t) gridDim.x / a.n_chunks;
+    const int step_y = (int) ((int64_t) gridDim.x - step_rows * a.n_chunks);
+    // the noise of a tile's row is fetched one tile ahead, like its samples
+    float noise_now = 0.0f;
+    if (tid < a.n_windows && (int64_t) blockIdx.x < total) noise_now = a.noise[row];
+    if (a.use_tma && a.two_buffers && tid == 0 && (int64_t) blockIdx.x < total) issue_tile(row, span_y, 0);
+
+    // ---- persistent loop over tiles; with two buffers the next tile's load is in flight while
+    //      this one is processed
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
+    const int buf = a.two_buffers ? (it & 1) : 0;
+    float *rowbuf = buf ? rowbuf1 : rowbuf0;
+    const int base = span_y * a.chunk_valid - a.edge;             // row channel of slot 0
+    const float *src = a.dev_t + row * a.dev_stride;
+    int64_t next_row = row + step_rows;
+    int next_y = span_y + step_y;
+    if (next_y >= a.n_chunks) {
+        next_y -= a.n_chunks;
+        next_row++;
+    }
+    const bool has_next = tile + gridDim.x < total;
+
+    // (everybody has left the previous tile's last barrier: thr, Fsm, stat and the other buffer
+    // are free)
+    if (tid < a.n_windows) {
+        thr[tid] = __double2float_rn((a.n_sigma * (double) noise_now) * a.scales[tid]);
+        if (has_next) noise_now = a.noise[next_row];
+    }
 
     // ---- stage the span (zeros outside the band)
     if (a.use_tma) {
-        // one TMA tile load: T runs of 128 bytes, swizzled, out-of-band runs zero-filled by the
-        // hardware; thread 0 issues it, everybody waits on the mbarrier
-        if (tid == 0) mbar_init(mbar, 1);
-        __syncthreads();
-        if (tid == 0) {
-            mbar_expect_tx(mbar, (uint32_t) span * 4u);
-            tma_load_3d(rowbuf, &tmap, 0, base >> 5, (int) row, mbar);
+        if (a.two_buffers) {
+            if (tid == 0 && has_next) issue_tile(next_row, next_y, buf ^ 1);
+            mbar_wait(&mbar[buf], (uint32_t) (it >> 1) & 1u);
+        } else {
+            if (tid == 0) issue_tile(row, span_y, 0);
+            mbar_wait(&mbar[0], (uint32_t) it & 1u);
         }
-        mbar_wait(mbar, 0);
     } else {
         const bool vec_ok = ((a.dev_stride & 3) == 0) &&
                             ((reinterpret_cast<uintptr_t>(a.dev_t) & 15) == 0) && ((base & 3) == 0) &&
@@ -250,8 +302,8 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
                 *reinterpret_cast<float4 *>(rowbuf + chunk_offset(q >> 3, q & 7)) = v;
             }
         }
-        __syncthreads();
     }
+    __syncthreads();                                           // thr[] (and the plain staging) visible
 
     // ---- my run: window size 1, then running sums of what is left
     const int my_sw = tid & 7;                                 // swizzle of my run
@@ -428,7 +480,7 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
 
 write_out:
     // ---- write my 32 flags if my run belongs to this block's output range
-    const int64_t out_lo = (int64_t) blockIdx.y * a.chunk_valid;
+    const int64_t out_lo = (int64_t) span_y * a.chunk_valid;
     const int64_t out_hi = min((int64_t) C, out_lo + (int64_t) a.chunk_valid);
     if (pos0 >= out_lo && pos0 < out_hi) {
         F &= in_range;
@@ -455,6 +507,9 @@ write_out:
             }
         }
     }
+    row = next_row;
+    span_y = next_y;
+    }   // tiles
 }
 
 // ---------------------------------------------------------------- ThresholdSimple
@@ -554,10 +609,28 @@ expand_flags_kernel(const uint32_t *__restrict__ bits_t, uint8_t *__restrict__ f
     }
 }
 
-size_t ts_smem_bytes(int threads)
+size_t ts_smem_bytes(int threads, int buffers)
 {
-    // + 1 KB so that the span can be aligned for the swizzle, + the mbarrier
-    return sizeof(float) * (((size_t) threads + 2) * PITCH + 7 * ((size_t) threads + 2) + 16) + 1024 + 16;
+    // span buffer(s), 7 words of state per run, thresholds and mbarriers, + 1 KB so that the
+    // spans can be aligned for the swizzle
+    return sizeof(float) * ((size_t) buffers * ((size_t) threads + 2) * PITCH + 7 * ((size_t) threads + 2) + 16) +
+           1024 + 16;
+}
+
+// Blocks of the persistent grid: as many as fit on the device at once.
+template <typename Kernel>
+int ts_launch(Kernel kernel, cudaStream_t s, const TsArgs &a, const CUtensorMap &tmap, int threads,
+              size_t smem)
+{
+    int per_sm = 0;
+    KSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t total = a.baselines * (int64_t) a.n_chunks;
+    int64_t blocks = (int64_t) per_sm * ksp_sm_count();
+    if (blocks > total) blocks = total;
+    kernel<<<(unsigned) blocks, threads, smem, s>>>(a, tmap);
+    KSP_CHECK_LAUNCH();
+    return 0;
 }
 
 int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise, uint8_t *flags_t,
@@ -607,9 +680,7 @@ int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise,
         a.chunk_valid = threads * RUN - 2 * a.edge;
         n_chunks = (int) ksp_divup(channels, a.chunk_valid);
     }
-    if (n_chunks > 65535) return KSP_ETOOLARGE;
-    dim3 grid((unsigned) baselines, (unsigned) n_chunks);
-    const size_t smem = ts_smem_bytes(threads);
+    a.n_chunks = n_chunks;
     // TMA staging: dev_t viewed as [baselines][channels / 32][32] floats, box = [1][threads][32],
     // 128-byte swizzle, zero fill outside the tensor (needs whole runs and 16-byte alignment)
     CUtensorMap tmap;
@@ -631,16 +702,16 @@ int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise,
                                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         a.use_tma = (rc == CUDA_SUCCESS) ? 1 : 0;
     }
-    // (the largest block needs less than the default 48 KB of dynamic shared memory)
+    // second span buffer while it fits in the default 48 KB of dynamic shared memory
+    a.two_buffers = (a.use_tma && ts_smem_bytes(threads, 2) <= 48 * 1024 &&
+                     baselines * (int64_t) n_chunks > 1) ? 1 : 0;
+    const size_t smem = ts_smem_bytes(threads, a.two_buffers ? 2 : 1);
     if (bits_t) {
-        if (threads == 128) threshold_sum_kernel<true, 128><<<grid, threads, smem, s>>>(a, tmap);
-        else threshold_sum_kernel<true, 0><<<grid, threads, smem, s>>>(a, tmap);
-    } else {
-        if (threads == 128) threshold_sum_kernel<false, 128><<<grid, threads, smem, s>>>(a, tmap);
-        else threshold_sum_kernel<false, 0><<<grid, threads, smem, s>>>(a, tmap);
+        if (threads == 128) return ts_launch(threshold_sum_kernel<true, 128>, s, a, tmap, threads, smem);
+        return ts_launch(threshold_sum_kernel<true, 0>, s, a, tmap, threads, smem);
     }
-    KSP_CHECK_LAUNCH();
-    return 0;
+    if (threads == 128) return ts_launch(threshold_sum_kernel<false, 128>, s, a, tmap, threads, smem);
+    return ts_launch(threshold_sum_kernel<false, 0>, s, a, tmap, threads, smem);
 }
 
 }  // namespace
