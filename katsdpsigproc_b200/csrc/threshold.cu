@@ -199,9 +199,11 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
 
     // two span buffers of (T + 2) * PITCH floats (the second only with two_buffers), then the
     // per-run state
+    // (each buffer starts on a 1 KB boundary: the swizzle is a function of the address)
+    const int buf_floats = (((T + 2) * PITCH + 255) / 256) * 256;
     float *rowbuf0 = sm;
-    float *rowbuf1 = rowbuf0 + (a.two_buffers ? (T + 2) * PITCH : 0);
-    float4 *stat = reinterpret_cast<float4 *>(rowbuf1 + (T + 2) * PITCH);   // T + 2: run statistics
+    float *rowbuf1 = rowbuf0 + (a.two_buffers ? buf_floats : 0);
+    float4 *stat = reinterpret_cast<float4 *>(rowbuf1 + buf_floats);        // T + 2: run statistics
     uint32_t *Fsm = reinterpret_cast<uint32_t *>(stat + T + 2);             // T + 2
     uint32_t *car1 = Fsm + T + 2;                              // T
     uint32_t *car2 = car1 + T;                                 // T
@@ -613,8 +615,8 @@ size_t ts_smem_bytes(int threads, int buffers)
 {
     // span buffer(s), 7 words of state per run, thresholds and mbarriers, + 1 KB so that the
     // spans can be aligned for the swizzle
-    return sizeof(float) * ((size_t) buffers * ((size_t) threads + 2) * PITCH + 7 * ((size_t) threads + 2) + 16) +
-           1024 + 16;
+    const size_t buf_floats = ((((size_t) threads + 2) * PITCH + 255) / 256) * 256;   // whole KB
+    return sizeof(float) * ((size_t) buffers * buf_floats + 7 * ((size_t) threads + 2) + 16) + 1024 + 16;
 }
 
 // Blocks of the persistent grid: as many as fit on the device at once.

@@ -207,6 +207,20 @@ def test_threshold_sum_long_rows(channels):
     check_sum(dev, noise, 3.0, 7, 1.2)
 
 
+@pytest.mark.parametrize("channels, baselines", [(12288, 700), (4096, 1300), (8192 + 32, 450)])
+def test_threshold_sum_many_tiles_per_block(channels, baselines):
+    """More (row, span) tiles than resident blocks: every block of the persistent grid walks
+    several tiles, alternating between its two span buffers."""
+    rs = np.random.RandomState(channels + baselines)
+    dev = rs.standard_normal((channels, baselines)).astype(np.float32)
+    for _ in range(baselines * 3):                       # interference of all widths, everywhere
+        bl, s = rs.randint(0, baselines), rs.randint(0, channels - 100)
+        dev[s:s + rs.randint(1, 100), bl] += rs.uniform(1.0, 6.0)
+    dev[rs.random_sample(dev.shape) < 1 / 64] += 40.0    # spikes
+    noise = rs.uniform(0.8, 1.3, baselines).astype(np.float32)
+    check_sum(dev, noise, 3.5, 7, 1.2)
+
+
 def test_threshold_sum_nan_noise_and_ties():
     dev = np.ones((64, 3), np.float32)
     noise = np.array([np.nan, 1.0 / 11.0, -1.0], np.float32)
@@ -230,6 +244,22 @@ def test_flagger_fused(golden, abs_mode, case, n_windows):
                                           chunk_baselines=32)
         assert_same_f32(noise, out_noise)
         np.testing.assert_array_equal(flags, out_flags)
+
+
+def test_flagger_fused_many_tiles(abs_mode):
+    """Enough (baseline, span) tiles that the persistent threshold blocks loop (packed output)."""
+    rs = np.random.RandomState(77)
+    channels, baselines = 8192, 300
+    vis = (rs.standard_normal((channels, baselines)) +
+           1j * rs.standard_normal((channels, baselines))).astype(np.complex64)
+    vis[rs.random_sample(vis.shape) < 1 / 64] += 60.0
+    for _ in range(200):
+        bl, s = rs.randint(0, baselines), rs.randint(0, channels - 70)
+        vis[s:s + rs.randint(2, 64), bl] += rs.uniform(2.0, 6.0)
+    flags, dev, noise = contract.flagger(vis, None, n_windows=7, n_sigma=4.0, abs_mode=abs_mode)
+    out_flags, out_noise = cu.flagger(vis, None, n_windows=7, n_sigma=4.0, abs_mode=abs_mode)
+    assert_same_f32(noise, out_noise)
+    np.testing.assert_array_equal(flags, out_flags)
 
 
 def test_flagger_fused_golden(golden, abs_mode):
