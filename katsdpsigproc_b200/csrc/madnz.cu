@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include "select.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -844,6 +845,365 @@ percentile5_stream_kernel(const void *__restrict__ src, float *__restrict__ dest
     }
 }
 
+// ------------------------------------------------------------------ Percentile5, fast path
+// The techniques of madnz_stream_kernel applied to three ranks at once, for rows that can be
+// read with aligned 16-byte loads (the usual case):
+//   1. 1024 x 16 bytes of the row are sampled (4096 amplitudes, or 2048 from complex input)
+//      into a two-level histogram over the float bit patterns; every warp locates the sample
+//      quantiles h either side of the 25 %, 50 % and 75 % ranks (h = 4.5 standard errors)
+//      and interpolates inside their bins: three disjoint brackets [lo_k, hi_k];
+//   2. ONE pass over the row with 16-byte loads, branch-free per element: min, max, a NaN
+//      detector, three predicated counters (a >= lo_k) and a predicated append of the
+//      elements inside any bracket (~20 %) to thread-private lists;
+//   3. one walk over the lists fills a two-level histogram per bracket, every warp locates the
+//      three wanted bins, a second walk collects their keys, warps 0..2 sort them.
+// Rows with NaN, overlapping brackets (heavy ties), a missed bracket, a crowded bin or a full
+// list fall back to the radix select over global memory, rank by rank.
+constexpr int PF_THREADS = 256;
+constexpr int PF_FINE = 1024;                 // histogram bins per bracket: 32 coarse x 32
+constexpr int PF_UNROLL = 4;                  // 16-byte loads in flight per thread
+
+// fine bin / rank lookup in a 32 x 32 two-level histogram (lane owns coarse bin `lane`)
+__device__ __forceinline__ BinHit locate_rank32(const uint32_t *coarse, const uint32_t *fine,
+                                                uint32_t r, int lane, uint32_t &total)
+{
+    const uint32_t c = coarse[lane];
+    const uint32_t c_incl = warp_scan_incl(c, lane), c_excl = c_incl - c;
+    total = __shfl_sync(0xffffffffu, c_incl, 31);
+    BinHit h = {0u, 0u, 0u};
+    if (r >= total) return h;                                  // warp-uniform: bracket missed
+    const int src = __ffs(__ballot_sync(0xffffffffu, r >= c_excl && r < c_incl)) - 1;
+    const uint32_t r_c = r - __shfl_sync(0xffffffffu, c_excl, src);
+    const uint32_t f = fine[src * 32 + lane];
+    const uint32_t f_incl = warp_scan_incl(f, lane), f_excl = f_incl - f;
+    const int src2 = __ffs(__ballot_sync(0xffffffffu, r_c >= f_excl && r_c < f_incl)) - 1;
+    h.bin = (uint32_t) (src * 32 + src2);
+    h.count = __shfl_sync(0xffffffffu, f, src2);
+    h.r_in = r_c - __shfl_sync(0xffffffffu, f_excl, src2);
+    return h;
+}
+
+// one element of the pass (amplitude a >= 0, not NaN): three counters, append if inside a bracket
+__device__ __forceinline__ void pf_step(float a, const float (&lo)[3], const float (&hi)[3],
+                                        uint32_t &ge0, uint32_t &ge1, uint32_t &ge2, uint32_t &slot)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred g0, g1, g2, i0, i1, i2;\n\t"
+        "setp.ge.f32 g0, %4, %5;\n\t"
+        "setp.ge.f32 g1, %4, %7;\n\t"
+        "setp.ge.f32 g2, %4, %9;\n\t"
+        "setp.le.and.f32 i0, %4, %6, g0;\n\t"
+        "setp.le.and.f32 i1, %4, %8, g1;\n\t"
+        "setp.le.and.f32 i2, %4, %10, g2;\n\t"
+        "or.pred i0, i0, i1;\n\t"
+        "or.pred i0, i0, i2;\n\t"
+        "@g0 add.u32 %0, %0, 1;\n\t"
+        "@g1 add.u32 %1, %1, 1;\n\t"
+        "@g2 add.u32 %2, %2, 1;\n\t"
+        "@i0 st.shared.f32 [%3], %4;\n\t"
+        "@i0 add.u32 %3, %3, %11;\n\t"
+        "}"
+        : "+r"(ge0), "+r"(ge1), "+r"(ge2), "+r"(slot)
+        : "f"(a), "f"(lo[0]), "f"(hi[0]), "f"(lo[1]), "f"(hi[1]), "f"(lo[2]), "f"(hi[2]),
+          "n"(PF_THREADS * 4));
+}
+
+__device__ __forceinline__ void pf_step_checked(float a, const float (&lo)[3], const float (&hi)[3],
+                                                uint32_t &ge0, uint32_t &ge1, uint32_t &ge2,
+                                                uint32_t &slot, uint32_t slot_end, bool &over)
+{
+    ge0 += (a >= lo[0]) ? 1u : 0u;
+    ge1 += (a >= lo[1]) ? 1u : 0u;
+    ge2 += (a >= lo[2]) ? 1u : 0u;
+    if ((a >= lo[0] && a <= hi[0]) || (a >= lo[1] && a <= hi[1]) || (a >= lo[2] && a <= hi[2])) {
+        if (slot < slot_end) {
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(slot), "f"(a));
+            slot += PF_THREADS * 4;
+        } else {
+            over = true;
+        }
+    }
+}
+
+template <int MODE>   // 0: float32 amplitudes, 1: complex64 numpy rule, 2: complex64 hypot rule
+__global__ void __launch_bounds__(PF_THREADS, 3)
+percentile5_fast_kernel(const void *__restrict__ src, float *__restrict__ dest, int64_t src_stride,
+                        int64_t dest_stride, int64_t first_col, int n, int slots, float half_width)
+{
+    constexpr int EPV = (MODE == 0) ? 4 : 2;                  // elements per 16-byte load
+    constexpr int ESZ = (MODE == 0) ? 4 : 8;
+    extern __shared__ __align__(16) uint32_t pf_smem[];
+    uint32_t *lists = pf_smem;                                // slots * 256 words
+    uint32_t *hist = lists + (size_t) slots * PF_THREADS;     // 3 * PF_FINE
+    uint32_t *coarse = hist + 3 * PF_FINE;                    // 3 * 32
+    uint32_t *small = coarse + 3 * 32;                        // 3 * 32
+    uint32_t *misc = small + 3 * 32;                          // 128 words
+    // misc: 0..2 counts of a >= lo_k, 3 list overflow, 4 min bits, 5 max bits, 6 NaN seen,
+    //       7..9 small-list counts, 10..12 results, 64..127 fallback scratch
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t off = (int64_t) blockIdx.x * src_stride + first_col;
+    const char *row = reinterpret_cast<const char *>(src) + off * ESZ;
+    const uint32_t nn = (uint32_t) n;
+    const uint32_t ranks[3] = {(nn - 1) / 4, (nn - 1) / 2, ((nn - 1) * 3) / 4};   // ascending
+
+    auto amplitudes = [](const float4 v, float (&a)[4]) {
+        if (MODE == 0) {
+            a[0] = fabsf(v.x); a[1] = fabsf(v.y); a[2] = fabsf(v.z); a[3] = fabsf(v.w);
+        } else {
+            a[0] = abs_c64<MODE == 1 ? KSP_ABS_NUMPY : KSP_ABS_HYPOT>(v.x, v.y);
+            a[1] = abs_c64<MODE == 1 ? KSP_ABS_NUMPY : KSP_ABS_HYPOT>(v.z, v.w);
+            a[2] = a[3] = 0.0f;
+        }
+    };
+    auto scalar_amplitude = [row](int i) -> float {
+        if (MODE == 0) return fabsf(reinterpret_cast<const float *>(row)[i]);
+        const float2 z = reinterpret_cast<const float2 *>(row)[i];
+        return abs_c64<MODE == 1 ? KSP_ABS_NUMPY : KSP_ABS_HYPOT>(z.x, z.y);
+    };
+
+    // ---- 1. brackets from a sample histogram (borrows the list memory)
+    uint32_t *s_fine = lists, *s_coarse = lists + MS_BINS;
+    for (int i = tid; i < MS_BINS; i += PF_THREADS) s_fine[i] = 0u;
+    for (int i = tid; i < 3 * PF_FINE; i += PF_THREADS) hist[i] = 0u;
+    if (tid < MS_BINS / 32) s_coarse[tid] = 0u;
+    if (tid < 3 * 32) coarse[tid] = 0u;
+    if (tid < 16) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
+    const int n_vec = n / EPV;
+    const float4 *row4 = reinterpret_cast<const float4 *>(row);
+    float4 sv[4];
+    {
+        const uint32_t step = (uint32_t) n_vec >> 10;
+#pragma unroll
+        for (int g = 0; g < 4; g++) {
+            const uint32_t i = (uint32_t) tid * 4u + g;
+            uint32_t pos = (uint32_t) (((uint64_t) i * (uint32_t) n_vec) >> 10);
+            pos += (((i * 2654435761u) >> 16) * step) >> 16;
+            sv[g] = __ldg(row4 + min((int) pos, n_vec - 1));
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        float a[4];
+        amplitudes(sv[g], a);
+#pragma unroll
+        for (int e = 0; e < EPV; e++) {
+            const uint32_t k = __float_as_uint(a[e]);
+            if (k <= KEY_INF) {                                // not NaN
+                atomicAdd(&s_fine[k >> 20], 1u);
+                atomicAdd(&s_coarse[k >> 25], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    uint32_t lo_k[3], hi_k[3];
+    bool degenerate;
+    {
+        const uint32_t c0 = s_coarse[2 * lane];
+        const uint32_t c01 = c0 + s_coarse[2 * lane + 1];
+        const uint32_t c_incl = warp_scan_incl(c01, lane), c_excl = c_incl - c01;
+        const uint32_t m = __shfl_sync(0xffffffffu, c_incl, 31);
+        degenerate = m == 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo_k[k] = 0u;
+            hi_k[k] = KEY_INF;
+            if (m > 0) {
+                const float q = (float) ranks[k] / (float) max(nn - 1u, 1u);
+                const float f_lo = (q - half_width) * (float) m, f_hi = (q + half_width) * (float) m;
+                if (f_lo >= 0.0f) {
+                    const BinHit b = locate_rank(s_coarse, s_fine, min((uint32_t) f_lo, m - 1u), c0, c_excl, lane);
+                    lo_k[k] = (b.bin << 20) + (uint32_t) (__fdividef((float) b.r_in, (float) b.count) * 1048576.0f);
+                }
+                if (f_hi < (float) (m - 1u)) {
+                    const BinHit b = locate_rank(s_coarse, s_fine, (uint32_t) ceilf(f_hi), c0, c_excl, lane);
+                    hi_k[k] = min((b.bin << 20) + (uint32_t) (__fdividef((float) (b.r_in + 1u), (float) b.count) * 1048576.0f),
+                                  KEY_INF);
+                }
+                hi_k[k] = max(hi_k[k], lo_k[k]);
+            }
+        }
+        degenerate |= !(hi_k[0] < lo_k[1] && hi_k[1] < lo_k[2]);
+    }
+    __syncthreads();                                           // the lists may overwrite the sample histogram
+
+    // ---- 2. one pass over the row
+    uint32_t n_mine = 0;
+    bool redo[3] = {degenerate, degenerate, degenerate};
+    if (!degenerate) {                                         // block-uniform
+        const float lo[3] = {__uint_as_float(lo_k[0]), __uint_as_float(lo_k[1]), __uint_as_float(lo_k[2])};
+        const float hi[3] = {__uint_as_float(hi_k[0]), __uint_as_float(hi_k[1]), __uint_as_float(hi_k[2])};
+        const uint32_t slot0 = (uint32_t) __cvta_generic_to_shared(lists + tid);
+        const uint32_t slot_end = slot0 + (uint32_t) slots * PF_THREADS * 4;
+        constexpr uint32_t BATCH_BYTES = PF_UNROLL * EPV * PF_THREADS * 4;
+        uint32_t ge0 = 0, ge1 = 0, ge2 = 0, slot = slot0;
+        float mn = __int_as_float(0x7f800000), mx = 0.0f, nan_acc = 0.0f;
+        bool over = false;
+        int i = tid;
+        for (; i + (PF_UNROLL - 1) * PF_THREADS < n_vec; i += PF_UNROLL * PF_THREADS) {
+            float4 v[PF_UNROLL];
+#pragma unroll
+            for (int u = 0; u < PF_UNROLL; u++) v[u] = __ldg(row4 + i + u * PF_THREADS);
+            const bool room = slot + BATCH_BYTES <= slot_end;
+#pragma unroll
+            for (int u = 0; u < PF_UNROLL; u++) {
+                float a[4];
+                amplitudes(v[u], a);
+#pragma unroll
+                for (int e = 0; e < EPV; e++) {
+                    mn = fminf(mn, a[e]);
+                    mx = fmaxf(mx, a[e]);
+                    nan_acc += a[e];
+                    if (room) pf_step(a[e], lo, hi, ge0, ge1, ge2, slot);
+                    else pf_step_checked(a[e], lo, hi, ge0, ge1, ge2, slot, slot_end, over);
+                }
+            }
+        }
+        for (; i < n_vec; i += PF_THREADS) {
+            float a[4];
+            amplitudes(__ldg(row4 + i), a);
+#pragma unroll
+            for (int e = 0; e < EPV; e++) {
+                mn = fminf(mn, a[e]);
+                mx = fmaxf(mx, a[e]);
+                nan_acc += a[e];
+                pf_step_checked(a[e], lo, hi, ge0, ge1, ge2, slot, slot_end, over);
+            }
+        }
+        for (int j = n_vec * EPV + tid; j < n; j += PF_THREADS) {
+            const float a = scalar_amplitude(j);
+            mn = fminf(mn, a);
+            mx = fmaxf(mx, a);
+            nan_acc += a;
+            pf_step_checked(a, lo, hi, ge0, ge1, ge2, slot, slot_end, over);
+        }
+        n_mine = (slot - slot0) / (PF_THREADS * 4);
+        ge0 = __reduce_add_sync(0xffffffffu, ge0);
+        ge1 = __reduce_add_sync(0xffffffffu, ge1);
+        ge2 = __reduce_add_sync(0xffffffffu, ge2);
+        const uint32_t mn_w = __reduce_min_sync(0xffffffffu, __float_as_uint(mn));
+        const uint32_t mx_w = __reduce_max_sync(0xffffffffu, __float_as_uint(mx));
+        const bool over_w = __any_sync(0xffffffffu, over);
+        const bool nan_w = __any_sync(0xffffffffu, nan_acc != nan_acc);
+        if (lane == 0) {
+            atomicAdd(&misc[0], ge0);
+            atomicAdd(&misc[1], ge1);
+            atomicAdd(&misc[2], ge2);
+            atomicMin(&misc[4], mn_w);
+            atomicMax(&misc[5], mx_w);
+            if (over_w) misc[3] = 1u;
+            if (nan_w) misc[6] = 1u;
+        }
+
+        // ---- 3. histograms of the three brackets in one walk over the lists
+        const uint32_t *mine = lists + tid;
+        int shift[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uint32_t width = hi_k[k] - lo_k[k] + 1u;
+            shift[k] = (width <= (uint32_t) PF_FINE) ? 0 : (32 - __clz(width - 1u)) - 10;
+        }
+        for (uint32_t j = 0; j < n_mine; j++) {
+            const uint32_t b = mine[j * PF_THREADS];
+            const int k = (b >= lo_k[1] ? 1 : 0) + (b >= lo_k[2] ? 1 : 0);
+            const uint32_t base = k == 0 ? lo_k[0] : (k == 1 ? lo_k[1] : lo_k[2]);
+            const int sh = k == 0 ? shift[0] : (k == 1 ? shift[1] : shift[2]);
+            const uint32_t bin = (b - base) >> sh;
+            atomicAdd(&hist[k * PF_FINE + bin], 1u);
+            atomicAdd(&coarse[k * 32 + (bin >> 5)], 1u);
+        }
+        __syncthreads();
+        const bool bad_row = (misc[3] | misc[6]) != 0u;        // full list or NaN: redo all three
+        BinHit hit[3];
+        bool collect[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            const uint32_t below = nn - misc[k];               // elements smaller than lo_k
+            const uint32_t r_rel = ranks[k] - below;           // wraps if the rank is below the bracket
+            uint32_t kept;
+            hit[k] = locate_rank32(coarse + k * 32, hist + k * PF_FINE, r_rel, lane, kept);
+            const bool missed = r_rel >= kept;
+            const bool crowded = shift[k] != 0 && hit[k].count > 32u;
+            redo[k] = bad_row || missed || crowded;
+            collect[k] = !redo[k] && shift[k] != 0;
+        }
+        // second walk: the keys of the three wanted bins
+        for (uint32_t j = 0; j < n_mine; j++) {
+            const uint32_t b = mine[j * PF_THREADS];
+            const int k = (b >= lo_k[1] ? 1 : 0) + (b >= lo_k[2] ? 1 : 0);
+            const uint32_t base = k == 0 ? lo_k[0] : (k == 1 ? lo_k[1] : lo_k[2]);
+            const int sh = k == 0 ? shift[0] : (k == 1 ? shift[1] : shift[2]);
+            const uint32_t want = k == 0 ? hit[0].bin : (k == 1 ? hit[1].bin : hit[2].bin);
+            const bool col = k == 0 ? collect[0] : (k == 1 ? collect[1] : collect[2]);
+            if (col && ((b - base) >> sh) == want) small[k * 32 + atomicAdd(&misc[7 + k], 1u)] = b;
+        }
+        __syncthreads();
+        if (warp < 3) {
+            const int k = warp;
+            const BinHit h = warp == 0 ? hit[0] : (warp == 1 ? hit[1] : hit[2]);
+            const bool rd = warp == 0 ? redo[0] : (warp == 1 ? redo[1] : redo[2]);
+            const int sh = warp == 0 ? shift[0] : (warp == 1 ? shift[1] : shift[2]);
+            const uint32_t base = warp == 0 ? lo_k[0] : (warp == 1 ? lo_k[1] : lo_k[2]);
+            if (!rd) {
+                uint32_t v;
+                if (sh == 0) {
+                    v = base + h.bin;
+                } else {
+                    const uint32_t srt = sort32(lane < (int) h.count ? small[k * 32 + lane] : 0xffffffffu, lane);
+                    v = __shfl_sync(0xffffffffu, srt, (int) h.r_in);
+                }
+                if (lane == 0) misc[10 + k] = v;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- fallbacks: radix select over the row in global memory (keys in float_to_key order)
+    uint32_t found[3];
+    uint32_t kmin = float_to_key(__uint_as_float(misc[4])), kmax = float_to_key(__uint_as_float(misc[5]));
+#pragma unroll
+    for (int k = 0; k < 3; k++) found[k] = float_to_key(__uint_as_float(misc[10 + k]));
+    if (redo[0] || redo[1] || redo[2]) {                       // block-uniform
+        __syncthreads();
+        SelectScratch sc;
+        sc.hist = lists;
+        sc.misc = misc + 64;
+        auto key_at = [&](int i) { return float_to_key(scalar_amplitude(i)); };
+#pragma unroll 1
+        for (int k = 0; k < 3; k++) {
+            if (!redo[k]) continue;
+            found[k] = block_radix_select<PF_THREADS>(key_at, n, ranks[k], sc);
+            if (tid == 0) atomicAdd(&g_selection_fallbacks, 1ull);
+        }
+        if (degenerate || misc[6] != 0u) {                     // min / max in key order (NaN sorts last)
+            uint32_t lo_key = 0xffffffffu, hi_key = 0u;
+            for (int i = tid; i < n; i += PF_THREADS) {
+                const uint32_t key = key_at(i);
+                lo_key = min(lo_key, key);
+                hi_key = max(hi_key, key);
+            }
+            lo_key = __reduce_min_sync(0xffffffffu, lo_key);
+            hi_key = __reduce_max_sync(0xffffffffu, hi_key);
+            __syncthreads();
+            if (tid == 0) { misc[64] = 0xffffffffu; misc[65] = 0u; }
+            __syncthreads();
+            if (lane == 0) { atomicMin(&misc[64], lo_key); atomicMax(&misc[65], hi_key); }
+            __syncthreads();
+            kmin = misc[64];
+            kmax = misc[65];
+        }
+    }
+    if (tid == 0) {
+        const int64_t r = blockIdx.x;
+        dest[0 * dest_stride + r] = key_to_float(kmin);
+        dest[1 * dest_stride + r] = key_to_float(kmax);
+        dest[2 * dest_stride + r] = key_to_float(found[0]);    // 25 %
+        dest[3 * dest_stride + r] = key_to_float(found[2]);    // 75 %
+        dest[4 * dest_stride + r] = key_to_float(found[1]);    // 50 %
+    }
+}
+
 int baselines_limit_ok(int64_t rows) { return rows > 0x7fffffff ? 1 : 0; }
 
 size_t select_smem_bytes(int64_t n, bool in_smem)
@@ -904,6 +1264,42 @@ extern "C" int ksp_percentile5(void *stream, const void *src, float *dest, int64
     if (abs_mode != KSP_ABS_NUMPY && abs_mode != KSP_ABS_HYPOT) return KSP_EINVAL;
     cudaStream_t s = (cudaStream_t) stream;
     if (baselines_limit_ok(rows) != 0) return KSP_ETOOLARGE;
+    // fast path: rows that can be read with aligned 16-byte loads and are long enough to sample
+    {
+        const size_t esz = is_amplitude ? 4 : 8;
+        const int epv = is_amplitude ? 4 : 2;
+        const bool aligned = ((uintptr_t) src % 16) == 0 && ((size_t) src_stride * esz) % 16 == 0 &&
+                             ((size_t) first_col * esz) % 16 == 0;
+        static const bool fast_allowed = [] {
+            const char *e = getenv("KSP_P5_FAST");
+            return !(e && atoi(e) == 0);
+        }();
+        if (fast_allowed && aligned && n_cols >= 8192) {
+            const double m = 1024.0 * epv;                          // samples
+            const double h = 4.5 * sqrt(0.25 / m);                  // bracket half-width (rank fraction)
+            const double frac = 6.0 * h + 3.0 / 1024.0;             // kept: three brackets + bin interpolation slack
+            const double per_t = (double) ksp_divup(n_cols, PF_THREADS);
+            int64_t fslots = (int64_t) (per_t * frac + 5.0 * sqrt(per_t * frac * (1.0 - frac)) + 4.0);
+            if (fslots * PF_THREADS < SELECT_HIST_WORDS) fslots = SELECT_HIST_WORDS / PF_THREADS;
+            const size_t fsmem = ((size_t) fslots * PF_THREADS + 3 * PF_FINE + 3 * 32 + 3 * 32 + 128) * sizeof(uint32_t);
+            if (fsmem <= 110 * 1024) {                              // 2-3 blocks per SM
+                const int mode = is_amplitude ? 0 : (abs_mode == KSP_ABS_NUMPY ? 1 : 2);
+#define KSP_PF_CASE(M)                                                                         \
+                if (mode == M) {                                                               \
+                    KSP_CUDA(cudaFuncSetAttribute(percentile5_fast_kernel<M>,                  \
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) fsmem)); \
+                    percentile5_fast_kernel<M><<<(unsigned) rows, PF_THREADS, fsmem, s>>>(     \
+                        src, dest, src_stride, dest_stride, first_col, (int) n_cols, (int) fslots, (float) h); \
+                }
+                KSP_PF_CASE(0)
+                KSP_PF_CASE(1)
+                KSP_PF_CASE(2)
+#undef KSP_PF_CASE
+                KSP_CHECK_LAUNCH();
+                return 0;
+            }
+        }
+    }
     // list slots per thread: the three brackets keep ~36 % of a thread's n / 256 keys
     const int64_t per_thread = ksp_divup(n_cols, P5_THREADS);
     int64_t slots = (per_thread * 36 + 99) / 100 + 5 * (int64_t) ceil(sqrt(0.23 * (double) per_thread)) + 4;

@@ -217,3 +217,10 @@ def flagger(vis: np.ndarray, input_flags: Optional[np.ndarray] = None, *, width:
     _capi.call("ksp_flagger", None, byref(p), dvis.p, fp, noise.p, flags.p, scratch.p,
                c_size_t(n_scratch))
     return flags.get(), noise.get()
+
+
+def selection_fallbacks(reset: bool = False) -> int:
+    """Rows (x ranks) that ksp_madnz_t / ksp_percentile5 redid with the radix select so far."""
+    count = ctypes.c_ulonglong(0)
+    _capi.call("ksp_selection_fallback_count", None, ctypes.byref(count), int(reset))
+    return int(count.value)

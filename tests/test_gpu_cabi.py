@@ -316,6 +316,39 @@ def test_percentile5(abs_mode, shape, column_range, is_amplitude):
         assert_same_f32(ref, out)
 
 
+@pytest.mark.parametrize("cols, column_range, pad", [(8192, None, 0), (16384, (8, 16380), 4),
+                                                     (32768, None, 0), (50000, (4, 49996), 0),
+                                                     (65536, None, 0)])
+@pytest.mark.parametrize("is_amplitude", [True, False])
+def test_percentile5_fast_path(abs_mode, cols, column_range, pad, is_amplitude):
+    """Rows readable with aligned 16-byte loads take the sampled-bracket kernel; the rows below
+    include everything that must push single ranks or whole rows onto its fallbacks.  (Rows
+    holding NaN are left out: their order statistics are unspecified, as in the reference.)"""
+    rs = np.random.RandomState(cols)
+    rows = 24
+    if is_amplitude:
+        src = np.abs(rs.standard_normal((rows, cols))).astype(np.float32)
+    else:
+        src = complex_normal(rs, (rows, cols))
+    src[1, rs.random_sample(cols) < 0.07] = 0                       # exact zeros
+    src[2] = np.round(src[2] * 4) / 4                               # heavy ties: overlapping brackets
+    src[3] = 1.5                                                    # constant row
+    src[4, 100] = 1e-38                                             # one denormal amplitude
+    src[5, 7] = np.inf
+    src[6] = src[6] * 1e-3 + 1.0                                    # narrow value range
+    src[7, : cols // 2] = 0                                         # half zeros: the 25 % rank is 0
+    src[8] = np.round(src[8] * 64) / 64                             # lighter ties: crowded bins
+    src[9] *= 1e-30                                                 # tiny values (denormal amplitudes)
+    src[10] *= 1e18                                                 # huge values
+    expect = contract.percentile5(src, column_range, abs_mode)
+    before = cu.selection_fallbacks(reset=True)
+    out = cu.percentile5(src, column_range, abs_mode, pad=pad)
+    fallbacks = cu.selection_fallbacks(reset=True)
+    assert_same_f32(expect, out)
+    # ordinary rows must not fall back: 13 of the 24 rows are plain noise
+    assert fallbacks <= 3 * 11 + 2, (before, fallbacks)
+
+
 def test_percentile5_golden(golden, abs_mode):
     assert_same_f32(golden["pct_amp_all"], cu.percentile5(golden["pct_in_amp"]))
     assert_same_f32(golden["pct_amp_range"], cu.percentile5(golden["pct_in_amp"], (10, 290)))
