@@ -76,6 +76,11 @@ def main():
         rec("background_t", timeit(lambda: _capi.call(
             "ksp_background_median_filter_t", S, p(vis), p(dev_t), None, C, B, B, CT, 0, 13, 0, 0, 0),
             args.reps, flush), 12)
+        amp = vis[..., 0].abs().contiguous()
+        rec("background_t_amplitude_input", timeit(lambda: _capi.call(
+            "ksp_background_median_filter_t", S, p(amp), p(dev_t), None, C, B, B, CT, 0, 13, 1, 0, 0),
+            args.reps, flush), 8)
+        del amp
         rec("transpose_f32", timeit(lambda: _capi.call(
             "ksp_transpose", S, p(dev_t), p(dev_cm), C, B, CT, B, 4), args.reps, flush), 8)
         rec("madnz_t", timeit(lambda: _capi.call(
