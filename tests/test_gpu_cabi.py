@@ -207,15 +207,17 @@ def test_threshold_sum_long_rows(channels):
     check_sum(dev, noise, 3.0, 7, 1.2)
 
 
-@pytest.mark.parametrize("channels, baselines", [(12288, 700), (4096, 1300), (8192 + 32, 450)])
+@pytest.mark.parametrize("channels, baselines", [(12288, 700), (4096, 1300), (8192 + 32, 450),
+                                                 (1024, 9000), (96, 20000), (2048 + 7, 3000)])
 def test_threshold_sum_many_tiles_per_block(channels, baselines):
     """More (row, span) tiles than resident blocks: every block of the persistent grid walks
     several tiles, alternating between its two span buffers."""
     rs = np.random.RandomState(channels + baselines)
     dev = rs.standard_normal((channels, baselines)).astype(np.float32)
     for _ in range(baselines * 3):                       # interference of all widths, everywhere
-        bl, s = rs.randint(0, baselines), rs.randint(0, channels - 100)
-        dev[s:s + rs.randint(1, 100), bl] += rs.uniform(1.0, 6.0)
+        wmax = min(100, channels // 2)
+        bl, s = rs.randint(0, baselines), rs.randint(0, channels - wmax)
+        dev[s:s + rs.randint(1, wmax), bl] += rs.uniform(1.0, 6.0)
     dev[rs.random_sample(dev.shape) < 1 / 64] += 40.0    # spikes
     noise = rs.uniform(0.8, 1.3, baselines).astype(np.float32)
     check_sum(dev, noise, 3.5, 7, 1.2)
