@@ -21,9 +21,9 @@ noise = torch.empty(B, device="cuda")
 flags = torch.empty(C, B, dtype=torch.uint8, device="cuda")
 p = lambda t: c_void_p(t.data_ptr())
 
-for lanes in (1, 2, 4):
+for lanes in (4, 8):
     os.environ["KSP_LANES"] = str(lanes)
-    for chunk in (148, 296, 592, 1184, 2080):
+    for chunk in (96, 192, 296, 592, 2368):
         prm = cu.flagger_params(C, B, B, B, n_windows=7, chunk_baselines=chunk)
         nbytes = _capi.load().ksp_flagger_scratch_bytes(byref(prm))
         scratch = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
