@@ -240,6 +240,9 @@ __device__ __forceinline__ bool tile_phase1(const BgArgs &a, int64_t b0, int c0,
 #ifndef BG_PF
 #define BG_PF 3
 #endif
+#ifndef BG_X8
+#define BG_X8 1                      // phase 2 computes 8 medians per step (median13x8)
+#endif
 template <int IN_MODE, int TC>
 __device__ __forceinline__ bool tile_phase1_pipelined(const BgArgs &a, int64_t b0, int c0, float *amp_sm)
 {
@@ -325,6 +328,60 @@ bg13_kernel(const BgArgs a)
         tile_bad = __syncthreads_or(any_bad);
     }
 
+#if BG_X8
+    // ---- phase 2, fast: no unusable sample anywhere in the tile.  Every thread produces runs of
+    // 8 outputs: the 6 samples common to all 8 windows are sorted once (median13x8).
+    if (!tile_bad) {
+        constexpr int RUNS8 = TC / 8;
+        for (int t = threadIdx.x; t < TILE_B * RUNS8; t += BG_THREADS) {
+            int bl, j;
+            if (TRANSPOSED) {
+                // lanes walk along channels, alternating between two baseline rows: 8 consecutive
+                // lanes then read 128-bit words from 8 different bank groups (rows are P = 276
+                // floats apart, 20 banks), and each row still gets 512 contiguous bytes per warp
+                bl = 2 * (t / (2 * RUNS8)) + (t & 1);
+                j = (t % (2 * RUNS8)) >> 1;
+            } else {                                              // lanes walk along baselines
+                j = t / TILE_B;
+                bl = t % TILE_B;
+            }
+            const float *src = amp_sm + bl * G::P + 8 * j;        // channel c - 8
+            float w[24];
+#pragma unroll
+            for (int k = 0; k < 6; k++) {
+                float4 q = *reinterpret_cast<const float4 *>(src + 4 * k);
+                w[4 * k] = q.x; w[4 * k + 1] = q.y; w[4 * k + 2] = q.z; w[4 * k + 3] = q.w;
+            }
+            float e[20];
+#pragma unroll
+            for (int k = 0; k < 20; k++) e[k] = w[k + 2];        // channels c-6 .. c+13
+            float m[8], o8[8];
+            median13x8(e, m);
+#pragma unroll
+            for (int k = 0; k < 8; k++) o8[k] = e[6 + k] - m[k];
+            const int c = c0 + 8 * j;
+            const int64_t b = b0 + bl;
+            if (b >= a.baselines || c >= C) continue;
+            if (TRANSPOSED) {
+                float *o = a.out + b * a.out_stride + c;
+                if (c + 7 < C && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                    reinterpret_cast<float4 *>(o)[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+                    reinterpret_cast<float4 *>(o)[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; k++)
+                        if (c + k < C) o[k] = o8[k];
+                }
+            } else {
+                float *o = a.out + c * a.out_stride + b;
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    if (c + k < C) o[k * a.out_stride] = o8[k];
+            }
+        }
+        return;
+    }
+#endif
     // ---- phase 2, fast: no unusable sample anywhere in the tile
     if (!tile_bad) {
         constexpr int RUNS = TC / 4;                 // runs of 4 outputs per baseline row

@@ -94,6 +94,66 @@ KSP_HD void median13x4(const float (&e)[16], int rot, float &o0, float &o1, floa
 #undef E
 }
 
+// Ranks 3..6 of the union of a sorted six a0<=..<=a5 and a sorted four b0<=..<=b3: Batcher's
+// odd-even merge pruned to the 16 min/max operations that reach those four outputs (derived
+// and verified over all sorted 0-1 inputs by tools/median_network.py).
+KSP_HD void mid4_of_sorted_6_4(float a0, float a1, float a2, float a3, float a4, float a5,
+                               float b0, float b1, float b2, float b3, float &m0, float &m1,
+                               float &m2, float &m3)
+{
+    b0 = fmaxf(a0, b0);
+    KSP_CE(a4, b0)
+    KSP_CE(a2, b2)
+    a4 = fmaxf(a2, a4);
+    b2 = fminf(b2, b0);
+    b1 = fmaxf(a1, b1);
+    a5 = fminf(a5, b1);
+    a3 = fminf(a3, b3);
+    KSP_CE(a3, a5)
+    KSP_CE(a3, a4)
+    KSP_CE(a5, b2)
+    m0 = a3; m1 = a4; m2 = a5; m3 = b2;
+}
+
+// Eight medians of 13 from 20 consecutive samples: out[j] = median(e[j .. j+12]), j = 0..7.
+// The windows of outputs 0..3 share e3..e12, those of outputs 4..7 share e7..e16; the six
+// samples e7..e12 common to all eight are sorted once, each group adds its own four:
+// 24 + 2 x (10 + 16) + 2 x 2 + 8 x 7 = 136 operations, 17 per output (median13x4: 21).
+// All 20 samples must be ordinary numbers (no NaN).
+KSP_HD void median13x8(const float (&e)[20], float (&o)[8])
+{
+    // sorted six e7..e12 (12 comparators)
+    float s0 = e[7], s1 = e[8], s2 = e[9], s3 = e[10], s4 = e[11], s5 = e[12];
+    KSP_CE(s0, s5) KSP_CE(s1, s3) KSP_CE(s2, s4)
+    KSP_CE(s1, s2) KSP_CE(s3, s4)
+    KSP_CE(s0, s3) KSP_CE(s2, s5)
+    KSP_CE(s0, s1) KSP_CE(s2, s3) KSP_CE(s4, s5)
+    KSP_CE(s1, s2) KSP_CE(s3, s4)
+    // group A: own four e3..e6; its first layer also sorts the pair (e5, e6) that group B needs
+    float a0 = e[3], a1 = e[4], a2 = e[5], a3 = e[6];
+    KSP_CE(a0, a1) KSP_CE(a2, a3)
+    const float pb0 = a2, pb1 = a3;                       // sorted (e5, e6)
+    KSP_CE(a0, a2) KSP_CE(a1, a3) KSP_CE(a1, a2)
+    // group B: own four e13..e16; its first layer sorts the pair (e13, e14) that group A needs
+    float b0 = e[13], b1 = e[14], b2 = e[15], b3 = e[16];
+    KSP_CE(b0, b1) KSP_CE(b2, b3)
+    const float qa0 = b0, qa1 = b1;                       // sorted (e13, e14)
+    KSP_CE(b0, b2) KSP_CE(b1, b3) KSP_CE(b1, b2)
+    float m0, m1, m2, m3;
+    mid4_of_sorted_6_4(s0, s1, s2, s3, s4, s5, a0, a1, a2, a3, m0, m1, m2, m3);
+    const float pa0 = fminf(e[1], e[2]), pa1 = fmaxf(e[1], e[2]);
+    o[0] = median7_core4_extras3(m0, m1, m2, m3, e[0], pa0, pa1);     // extras e0, e1, e2
+    o[1] = median7_core4_extras3(m0, m1, m2, m3, e[13], pa0, pa1);    // extras e1, e2, e13
+    o[2] = median7_core4_extras3(m0, m1, m2, m3, e[2], qa0, qa1);     // extras e2, e13, e14
+    o[3] = median7_core4_extras3(m0, m1, m2, m3, e[15], qa0, qa1);    // extras e13, e14, e15
+    mid4_of_sorted_6_4(s0, s1, s2, s3, s4, s5, b0, b1, b2, b3, m0, m1, m2, m3);
+    const float qb0 = fminf(e[17], e[18]), qb1 = fmaxf(e[17], e[18]);
+    o[4] = median7_core4_extras3(m0, m1, m2, m3, e[4], pb0, pb1);     // extras e4, e5, e6
+    o[5] = median7_core4_extras3(m0, m1, m2, m3, e[17], pb0, pb1);    // extras e5, e6, e17
+    o[6] = median7_core4_extras3(m0, m1, m2, m3, e[6], qb0, qb1);     // extras e6, e17, e18
+    o[7] = median7_core4_extras3(m0, m1, m2, m3, e[19], qb0, qb1);    // extras e17, e18, e19
+}
+
 // Generic median of up to 13 samples with a validity mask (bit k <-> w[k]).
 // Returns false if no sample is valid.  lo/hi are the lower/upper medians (equal
 // when the count is odd).  Slow path: ~250 operations.

@@ -44,7 +44,51 @@ def check_pruned(prog, n, keep):
         if any(v[k] != s[k] for k in keep): return False
     return True
 
+def odd_even_merge(a, b, net):
+    """Batcher's odd-even merge of two sorted wire lists; appends comparators to `net` and
+    returns the wires in output order."""
+    if not a: return list(b)
+    if not b: return list(a)
+    if len(a) == 1 and len(b) == 1:
+        net.append((a[0], b[0]))
+        return [a[0], b[0]]
+    ev = odd_even_merge(a[0::2], b[0::2], net)
+    od = odd_even_merge(a[1::2], b[1::2], net)
+    out, rest = [ev[0]], ev[1:]
+    k = min(len(od), len(rest))
+    for i in range(k):
+        net.append((od[i], rest[i]))
+        out += [od[i], rest[i]]
+    return out + od[k:] + rest[k:]
+
+def merge_6_4_mid4():
+    """Ranks 3..6 of sorted six U sorted four (median13x8): pruned merge, checked on all
+    sorted 0-1 inputs."""
+    net = []
+    out = odd_even_merge(list(range(6)), list(range(6, 10)), net)
+    live, prog = set(out[3:7]), []
+    for p, q in reversed(net):
+        mn, mx = p in live, q in live
+        if mn or mx:
+            prog.append((p, q, mn, mx)); live.add(p); live.add(q)
+    prog.reverse()
+    for ka in range(7):
+        for kb in range(5):
+            bits = [0] * (6 - ka) + [1] * ka + [0] * (4 - kb) + [1] * kb
+            v = list(bits)
+            for p, q, mn, mx in prog:
+                lo, hi = min(v[p], v[q]), max(v[p], v[q])
+                if mn: v[p] = lo
+                if mx: v[q] = hi
+            assert [v[w] for w in out[3:7]] == sorted(bits)[3:7]
+    name = lambda i: f"a{i}" if i < 6 else f"b{i - 6}"
+    print("merge(6,4) -> ranks 3..6:", sum(mn + mx for _, _, mn, mx in prog), "min/max ops; outputs on",
+          [name(w) for w in out[3:7]])
+    for p, q, mn, mx in prog:
+        print(f"  ({name(p)},{name(q)}) {'min' if mn else '   '} {'max' if mx else '   '}")
+
 if __name__ == "__main__":
+    merge_6_4_mid4()
     assert sorts(NET10, 10)
     prog = prune(NET10, 10, [3,4,5,6])
     assert check_pruned(prog, 10, [3,4,5,6])

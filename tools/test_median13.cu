@@ -24,6 +24,16 @@ int main()
             std::sort(w.begin(), w.end());
             if (w[6] != o[j]) bad++;
         }
+        {   // eight medians from 20 samples
+            float e20[20], o8[8];
+            for (int k = 0; k < 20; k++) e20[k] = (float) (rand() % mod) * 0.37f;
+            ksp::median13x8(e20, o8);
+            for (int j = 0; j < 8; j++) {
+                std::vector<float> w(e20 + j, e20 + j + 13);
+                std::sort(w.begin(), w.end());
+                if (w[6] != o8[j]) bad++;
+            }
+        }
         float w13[13];
         for (int k = 0; k < 13; k++) w13[k] = e[k];
         unsigned valid = (unsigned) rand() & 0x1fff;
