@@ -545,6 +545,210 @@ madnz_cm_kernel(const float *__restrict__ dev, float *__restrict__ noise, int ch
     }
 }
 
+// Channel-major MAD in three passes (rows of at most 65535 channels): radix select with digits
+// of 11, 11 and 9 bits instead of four of 8, the count of usable samples folded into the first
+// pass and the "next key above" of even counts into the last.  The histogram
+// hist[digit][baseline] holds 2048 x 32 counters as 16-bit halves of 1024 x 32 words
+// (digit d -> word row d & 1023, half d >> 10; the column is skewed by the row so that both the
+// atomics of a warp - lane == baseline - and the resolving warp's reads spread over the banks).
+constexpr int CM3_ROWS = 1024;
+
+// rank lookup for baseline `bl` by one warp: walks the digits 32 at a time (digit = 32 i + lane).
+// Returns the digit holding `rank`, the rank inside it, its count and the next non-empty digit
+// above it (n_digits if none).
+struct Cm3Hit { uint32_t digit, r_in, count, next; };
+__device__ __forceinline__ Cm3Hit cm3_locate(const uint32_t *hist, int bl, uint32_t rank, int n_digits,
+                                             int lane)
+{
+    Cm3Hit h = {0u, 0u, 0u, (uint32_t) n_digits};
+    bool found = false;
+    uint32_t remaining = rank;
+    for (int i = 0; i < n_digits / 32; i++) {
+        const int d = 32 * i + lane;
+        const int r = d & (CM3_ROWS - 1);
+        const uint32_t word = hist[r * 32 + ((bl + r) & 31)];
+        const uint32_t c = (d >> 10) ? (word >> 16) : (word & 0xffffu);
+        if (!found) {
+            const uint32_t incl = warp_scan_incl(c, lane);
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            if (remaining < total) {
+                const int src = __ffs(__ballot_sync(0xffffffffu, remaining < incl)) - 1;
+                h.digit = (uint32_t) (32 * i + src);
+                h.count = __shfl_sync(0xffffffffu, c, src);
+                h.r_in = remaining - (__shfl_sync(0xffffffffu, incl, src) - h.count);
+                found = true;
+                // next non-empty digit inside this group of 32
+                const uint32_t above = __ballot_sync(0xffffffffu, c != 0u && lane > src);
+                if (above) {
+                    h.next = (uint32_t) (32 * i + __ffs(above) - 1);
+                    break;
+                }
+            } else {
+                remaining -= total;
+            }
+        } else {
+            const uint32_t nz = __ballot_sync(0xffffffffu, c != 0u);
+            if (nz) {
+                h.next = (uint32_t) (32 * i + __ffs(nz) - 1);
+                break;
+            }
+        }
+    }
+    return h;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+madnz_cm3_kernel(const float *__restrict__ dev, float *__restrict__ noise, int channels,
+                 int baselines, int64_t stride)
+{
+    extern __shared__ uint32_t cm_hist[];              // CM3_ROWS x 32 words
+    __shared__ uint32_t part[32][33];                  // per-warp partials
+    __shared__ uint32_t s_prefix[32], s_rank[32], s_nvalid[32], s_rin[32], s_cnt[32], s_next[32];
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b_raw = blockIdx.x * 32 + lane;
+    const bool ok = b_raw < baselines;
+    const int b = ok ? b_raw : baselines - 1;
+    const float *col = dev + b;
+
+    auto clear = [&]() {
+        for (int i = threadIdx.x; i < CM3_ROWS * 32; i += 1024) cm_hist[i] = 0u;
+    };
+    auto bump = [&](uint32_t d) {
+        const uint32_t r = d & (CM3_ROWS - 1);
+        atomicAdd(&cm_hist[r * 32 + ((lane + r) & 31)], (d >> 10) ? 0x10000u : 1u);
+    };
+
+    // ---- pass 1: usable count and the top 11 bits (keys are at most 0x7f800000: digit < 2048)
+    clear();
+    __syncthreads();
+    {
+        uint32_t cnt = 0;
+        int c = warp;
+        for (; c + 96 < channels; c += 128) {
+            uint32_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) k[u] = mad_key(col[(int64_t) (c + 32 * u) * stride]);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k[u] != KEY_SKIP) { cnt++; bump(k[u] >> 20); }
+        }
+        for (; c < channels; c += 32) {
+            const uint32_t k = mad_key(col[(int64_t) c * stride]);
+            if (k != KEY_SKIP) { cnt++; bump(k >> 20); }
+        }
+        part[warp][lane] = cnt;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < 32; w++) t += part[w][lane];
+        s_nvalid[lane] = t;
+        s_rank[lane] = t ? (t - 1) >> 1 : 0;
+    }
+    __syncthreads();
+    {
+        const int bl = warp;                            // warp w resolves baseline w
+        if (s_nvalid[bl] != 0) {
+            const Cm3Hit h = cm3_locate(cm_hist, bl, s_rank[bl], 2048, lane);
+            if (lane == 0) { s_prefix[bl] = h.digit << 20; s_rank[bl] = h.r_in; }
+        } else if (lane == 0) {
+            s_prefix[bl] = 0u;
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 2: the next 11 bits among the keys that share the first digit
+    clear();
+    __syncthreads();
+    {
+        const uint32_t want = s_prefix[lane] >> 20;
+        int c = warp;
+        for (; c + 96 < channels; c += 128) {
+            uint32_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) k[u] = mad_key(col[(int64_t) (c + 32 * u) * stride]);
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k[u] != KEY_SKIP && (k[u] >> 20) == want) bump((k[u] >> 9) & 0x7ffu);
+        }
+        for (; c < channels; c += 32) {
+            const uint32_t k = mad_key(col[(int64_t) c * stride]);
+            if (k != KEY_SKIP && (k >> 20) == want) bump((k >> 9) & 0x7ffu);
+        }
+    }
+    __syncthreads();
+    {
+        const int bl = warp;
+        if (s_nvalid[bl] != 0) {
+            const Cm3Hit h = cm3_locate(cm_hist, bl, s_rank[bl], 2048, lane);
+            if (lane == 0) { s_prefix[bl] |= h.digit << 9; s_rank[bl] = h.r_in; }
+        }
+    }
+    __syncthreads();
+
+    // ---- pass 3: the last 9 bits; also the smallest key beyond the 22-bit prefix
+    clear();
+    __syncthreads();
+    {
+        const uint32_t want = s_prefix[lane] >> 9;
+        uint32_t beyond = KEY_SKIP;
+        int c = warp;
+        for (; c + 96 < channels; c += 128) {
+            uint32_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) k[u] = mad_key(col[(int64_t) (c + 32 * u) * stride]);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if (k[u] == KEY_SKIP) continue;
+                const uint32_t p = k[u] >> 9;
+                if (p == want) bump(k[u] & 0x1ffu);
+                else if (p > want) beyond = min(beyond, k[u]);
+            }
+        }
+        for (; c < channels; c += 32) {
+            const uint32_t k = mad_key(col[(int64_t) c * stride]);
+            if (k == KEY_SKIP) continue;
+            const uint32_t p = k >> 9;
+            if (p == want) bump(k & 0x1ffu);
+            else if (p > want) beyond = min(beyond, k);
+        }
+        part[warp][lane] = beyond;
+    }
+    __syncthreads();
+    {
+        const int bl = warp;
+        if (s_nvalid[bl] != 0) {
+            const Cm3Hit h = cm3_locate(cm_hist, bl, s_rank[bl], 512, lane);
+            if (lane == 0) {
+                const uint32_t p22 = s_prefix[bl];
+                s_prefix[bl] = p22 | h.digit;
+                s_rin[bl] = h.r_in;
+                s_cnt[bl] = h.count;
+                s_next[bl] = h.next < 512u ? (p22 | h.next) : KEY_SKIP;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && ok) {
+        const uint32_t n = s_nvalid[lane];
+        float out = __int_as_float(0x7fc00000);
+        if (n) {
+            const uint32_t lo = s_prefix[lane];
+            uint32_t hi = lo;
+            // even count: the upper median is another copy of lo unless lo is the last of its value
+            if (!(n & 1u) && s_rin[lane] + 1u == s_cnt[lane]) {
+                hi = s_next[lane];
+                if (hi == KEY_SKIP) {
+                    for (int w = 0; w < 32; w++) hi = min(hi, part[w][lane]);
+                }
+            }
+            out = mad_finish(lo, hi);
+        }
+        noise[b_raw] = out;
+    }
+}
+
 // ------------------------------------------------------------------ Percentile5
 template <bool IN_SMEM>
 __global__ void __launch_bounds__(SEL_THREADS, 1)
@@ -1245,6 +1449,15 @@ extern "C" int ksp_madnz(void *stream, const float *dev, float *noise, int64_t c
     if (baselines == 0) return 0;
     if (!dev || !noise) return KSP_EINVAL;
     if (channels > (int64_t) 1 << 30 || baselines > (int64_t) 1 << 30) return KSP_ETOOLARGE;
+    if (channels <= 65535) {                                 // 16-bit counters suffice
+        const size_t smem = (size_t) CM3_ROWS * 32 * sizeof(uint32_t);
+        KSP_CUDA(cudaFuncSetAttribute(madnz_cm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int) smem));
+        madnz_cm3_kernel<<<(unsigned) ksp_divup(baselines, 32), 1024, smem, (cudaStream_t) stream>>>(
+            dev, noise, (int) channels, (int) baselines, stride);
+        KSP_CHECK_LAUNCH();
+        return 0;
+    }
     madnz_cm_kernel<<<(unsigned) ksp_divup(baselines, 32), 1024, 0, (cudaStream_t) stream>>>(
         dev, noise, (int) channels, (int) baselines, stride);
     KSP_CHECK_LAUNCH();

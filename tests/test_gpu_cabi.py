@@ -125,7 +125,7 @@ def test_madnz(golden, transposed):
 
 
 @pytest.mark.parametrize("transposed", [False, True])
-@pytest.mark.parametrize("channels", [1, 2, 6, 1000, 10000, 10001, 40000, 70001])
+@pytest.mark.parametrize("channels", [1, 2, 6, 1000, 10000, 10001, 40000, 65535, 65536, 70001])
 def test_madnz_sizes(transposed, channels):
     rs = np.random.RandomState(channels)
     baselines = 5
