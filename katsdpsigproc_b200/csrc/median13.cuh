@@ -77,6 +77,18 @@ KSP_HD float median7_core4_extras3(float m0, float m1, float m2, float m3, float
     return fminf(ksp_min3(t0, t1, t2), m3);
 }
 
+// Two medians of 7 that share six of their values: {m0<=m1<=m2<=m3} U {p0<=p1} U {x} for
+// x = xa, xb.  With r2 <= r3 the 3rd and 4th smallest of the six, the median is clamp(x, r2, r3):
+// 6 operations for the pair of bounds, 2 per output.
+KSP_HD void median7_pair(float m0, float m1, float m2, float m3, float p0, float p1, float xa,
+                         float xb, float &oa, float &ob)
+{
+    const float r2 = ksp_min3(fmaxf(m0, p1), fmaxf(m1, p0), m2);
+    const float r3 = ksp_min3(fmaxf(m1, p1), fmaxf(m2, p0), m3);
+    oa = fmaxf(r2, fminf(xa, r3));
+    ob = fmaxf(r2, fminf(xb, r3));
+}
+
 // Four medians of 13 from 16 consecutive samples: out[j] = median(e[j .. j+12]).
 // All 16 samples must be ordinary numbers (no NaN).
 KSP_HD void median13x4(const float (&e)[16], int rot, float &o0, float &o1, float &o2, float &o3)
@@ -87,10 +99,8 @@ KSP_HD void median13x4(const float (&e)[16], int rot, float &o0, float &o1, floa
     // left extras {e0,e1,e2} / {e1,e2}; right extras {e13,e14} / {e13,e14,e15}
     const float p0 = fminf(E(1), E(2)), p1 = fmaxf(E(1), E(2));
     const float q0 = fminf(E(13), E(14)), q1 = fmaxf(E(13), E(14));
-    o0 = median7_core4_extras3(m0, m1, m2, m3, E(0), p0, p1);    // extras e0, e1, e2
-    o1 = median7_core4_extras3(m0, m1, m2, m3, E(13), p0, p1);   // extras e1, e2, e13
-    o2 = median7_core4_extras3(m0, m1, m2, m3, E(2), q0, q1);    // extras e2, e13, e14
-    o3 = median7_core4_extras3(m0, m1, m2, m3, E(15), q0, q1);   // extras e13, e14, e15
+    median7_pair(m0, m1, m2, m3, p0, p1, E(0), E(13), o0, o1);   // extras e0,e1,e2 / e1,e2,e13
+    median7_pair(m0, m1, m2, m3, q0, q1, E(2), E(15), o2, o3);   // extras e2,e13,e14 / e13,e14,e15
 #undef E
 }
 
@@ -118,7 +128,9 @@ KSP_HD void mid4_of_sorted_6_4(float a0, float a1, float a2, float a3, float a4,
 // Eight medians of 13 from 20 consecutive samples: out[j] = median(e[j .. j+12]), j = 0..7.
 // The windows of outputs 0..3 share e3..e12, those of outputs 4..7 share e7..e16; the six
 // samples e7..e12 common to all eight are sorted once, each group adds its own four:
-// 24 + 2 x (10 + 16) + 2 x 2 + 8 x 7 = 136 operations, 17 per output (median13x4: 21).
+// the three samples particular to an output are a sorted pair shared with its neighbour plus
+// one more: 24 + 2 x (10 + 16) + 2 x 2 + 4 x 6 + 8 x 2 = 120 operations, 15 per output
+// (median13x4: 21).
 // All 20 samples must be ordinary numbers (no NaN).
 KSP_HD void median13x8(const float (&e)[20], float (&o)[8])
 {
@@ -142,16 +154,12 @@ KSP_HD void median13x8(const float (&e)[20], float (&o)[8])
     float m0, m1, m2, m3;
     mid4_of_sorted_6_4(s0, s1, s2, s3, s4, s5, a0, a1, a2, a3, m0, m1, m2, m3);
     const float pa0 = fminf(e[1], e[2]), pa1 = fmaxf(e[1], e[2]);
-    o[0] = median7_core4_extras3(m0, m1, m2, m3, e[0], pa0, pa1);     // extras e0, e1, e2
-    o[1] = median7_core4_extras3(m0, m1, m2, m3, e[13], pa0, pa1);    // extras e1, e2, e13
-    o[2] = median7_core4_extras3(m0, m1, m2, m3, e[2], qa0, qa1);     // extras e2, e13, e14
-    o[3] = median7_core4_extras3(m0, m1, m2, m3, e[15], qa0, qa1);    // extras e13, e14, e15
+    median7_pair(m0, m1, m2, m3, pa0, pa1, e[0], e[13], o[0], o[1]);  // extras e0,e1,e2 / e1,e2,e13
+    median7_pair(m0, m1, m2, m3, qa0, qa1, e[2], e[15], o[2], o[3]);  // extras e2,e13,e14 / e13,e14,e15
     mid4_of_sorted_6_4(s0, s1, s2, s3, s4, s5, b0, b1, b2, b3, m0, m1, m2, m3);
     const float qb0 = fminf(e[17], e[18]), qb1 = fmaxf(e[17], e[18]);
-    o[4] = median7_core4_extras3(m0, m1, m2, m3, e[4], pb0, pb1);     // extras e4, e5, e6
-    o[5] = median7_core4_extras3(m0, m1, m2, m3, e[17], pb0, pb1);    // extras e5, e6, e17
-    o[6] = median7_core4_extras3(m0, m1, m2, m3, e[6], qb0, qb1);     // extras e6, e17, e18
-    o[7] = median7_core4_extras3(m0, m1, m2, m3, e[19], qb0, qb1);    // extras e17, e18, e19
+    median7_pair(m0, m1, m2, m3, pb0, pb1, e[4], e[17], o[4], o[5]);  // extras e4,e5,e6 / e5,e6,e17
+    median7_pair(m0, m1, m2, m3, qb0, qb1, e[6], e[19], o[6], o[7]);  // extras e6,e17,e18 / e17,e18,e19
 }
 
 // Generic median of up to 13 samples with a validity mask (bit k <-> w[k]).
