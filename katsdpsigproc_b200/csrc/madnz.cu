@@ -1302,18 +1302,19 @@ percentile5_fast_kernel(const void *__restrict__ src, float *__restrict__ dest, 
 
         // ---- 3. histograms of the three brackets in one walk over the lists
         const uint32_t *mine = lists + tid;
-        int shift[3];
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-            const uint32_t width = hi_k[k] - lo_k[k] + 1u;
-            shift[k] = (width <= (uint32_t) PF_FINE) ? 0 : (32 - __clz(width - 1u)) - 10;
+        // one bin width for the three brackets (that of the widest), so that a key only has to
+        // find its bracket's origin: key - origin_k >> shift, histogram k
+        int shift;
+        {
+            const uint32_t widest = max(max(hi_k[0] - lo_k[0], hi_k[1] - lo_k[1]), hi_k[2] - lo_k[2]) + 1u;
+            shift = (widest <= (uint32_t) PF_FINE) ? 0 : (32 - __clz(widest - 1u)) - 10;
         }
+        const uint32_t d01 = lo_k[1] - lo_k[0], d12 = lo_k[2] - lo_k[1];
         for (uint32_t j = 0; j < n_mine; j++) {
             const uint32_t b = mine[j * PF_THREADS];
-            const int k = (b >= lo_k[1] ? 1 : 0) + (b >= lo_k[2] ? 1 : 0);
-            const uint32_t base = k == 0 ? lo_k[0] : (k == 1 ? lo_k[1] : lo_k[2]);
-            const int sh = k == 0 ? shift[0] : (k == 1 ? shift[1] : shift[2]);
-            const uint32_t bin = (b - base) >> sh;
+            const uint32_t in1 = b >= lo_k[1] ? 1u : 0u, in2 = b >= lo_k[2] ? 1u : 0u;
+            const uint32_t k = in1 + in2;
+            const uint32_t bin = (b - lo_k[0] - in1 * d01 - in2 * d12) >> shift;
             atomicAdd(&hist[k * PF_FINE + bin], 1u);
             atomicAdd(&coarse[k * 32 + (bin >> 5)], 1u);
         }
@@ -1328,26 +1329,30 @@ percentile5_fast_kernel(const void *__restrict__ src, float *__restrict__ dest, 
             uint32_t kept;
             hit[k] = locate_rank32(coarse + k * 32, hist + k * PF_FINE, r_rel, lane, kept);
             const bool missed = r_rel >= kept;
-            const bool crowded = shift[k] != 0 && hit[k].count > 32u;
+            const bool crowded = shift != 0 && hit[k].count > 32u;
             redo[k] = bad_row || missed || crowded;
-            collect[k] = !redo[k] && shift[k] != 0;
+            collect[k] = !redo[k] && shift != 0;
         }
         // second walk: the keys of the three wanted bins
+        // second walk: the keys of the three wanted bins.  A bracket that is not collected gets
+        // an impossible bin number; (histogram, bin) is compared as one word.
+        const uint32_t want0 = collect[0] ? hit[0].bin : 0xffffu;
+        const uint32_t want1 = (1u << 16) | (collect[1] ? hit[1].bin : 0xffffu);
+        const uint32_t want2 = (2u << 16) | (collect[2] ? hit[2].bin : 0xffffu);
         for (uint32_t j = 0; j < n_mine; j++) {
             const uint32_t b = mine[j * PF_THREADS];
-            const int k = (b >= lo_k[1] ? 1 : 0) + (b >= lo_k[2] ? 1 : 0);
-            const uint32_t base = k == 0 ? lo_k[0] : (k == 1 ? lo_k[1] : lo_k[2]);
-            const int sh = k == 0 ? shift[0] : (k == 1 ? shift[1] : shift[2]);
-            const uint32_t want = k == 0 ? hit[0].bin : (k == 1 ? hit[1].bin : hit[2].bin);
-            const bool col = k == 0 ? collect[0] : (k == 1 ? collect[1] : collect[2]);
-            if (col && ((b - base) >> sh) == want) small[k * 32 + atomicAdd(&misc[7 + k], 1u)] = b;
+            const uint32_t in1 = b >= lo_k[1] ? 1u : 0u, in2 = b >= lo_k[2] ? 1u : 0u;
+            const uint32_t k = in1 + in2;
+            const uint32_t tag = (k << 16) | ((b - lo_k[0] - in1 * d01 - in2 * d12) >> shift);
+            if (tag == want0 || tag == want1 || tag == want2)
+                small[k * 32 + atomicAdd(&misc[7 + k], 1u)] = b;
         }
         __syncthreads();
         if (warp < 3) {
             const int k = warp;
             const BinHit h = warp == 0 ? hit[0] : (warp == 1 ? hit[1] : hit[2]);
             const bool rd = warp == 0 ? redo[0] : (warp == 1 ? redo[1] : redo[2]);
-            const int sh = warp == 0 ? shift[0] : (warp == 1 ? shift[1] : shift[2]);
+            const int sh = shift;
             const uint32_t base = warp == 0 ? lo_k[0] : (warp == 1 ? lo_k[1] : lo_k[2]);
             if (!rd) {
                 uint32_t v;
