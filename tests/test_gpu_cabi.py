@@ -85,6 +85,25 @@ def test_background_small_and_long(abs_mode, shape, transposed):
         assert_same_f32(expect, out.T if transposed else out)
 
 
+@pytest.mark.parametrize("width", [3, 7, 9, 11, 15, 21, 31, 33, 63])
+@pytest.mark.parametrize("transposed", [False, True])
+def test_background_other_widths(abs_mode, width, transposed):
+    """Odd widths up to 31 take the sliding-sorted-window kernel, wider ones the generic one;
+    clean tiles, tiles with flags / NaN, band edges and a ragged last tile in both directions."""
+    vis, flags = bg_inputs(700, 45, seed=width)
+    vis[350:420, 11:] *= 3.0
+    vis[500, 2] = np.nan
+    for fl in (None, np.ascontiguousarray(flags[:, 3]), flags):
+        expect = contract.background(vis, width, fl, False, abs_mode)
+        out = cu.background(vis, width, fl, False, abs_mode, transposed, pad=3)
+        assert_same_f32(expect, out.T if transposed else out)
+    amp = np.abs(vis)
+    amp[np.isnan(amp)] = 1.0
+    expect = contract.background(amp, width, None, True, abs_mode)
+    out = cu.background(amp, width, None, True, abs_mode, transposed)
+    assert_same_f32(expect, out.T if transposed else out)
+
+
 def test_background_special_values(abs_mode):
     rs = np.random.RandomState(4)
     vis = complex_normal(rs, (300, 40))

@@ -362,8 +362,8 @@ def test_streaming_flagger(context, abs_mode, depth, use_flags):
 
 @pytest.mark.parametrize("depth", [1, 3])
 def test_async_streaming_flagger(context, abs_mode, depth):
-    """The asyncio pipeline (Resource / JobQueue / async_wait_for_events): results arrive in
-    submission order and equal the oracle while the producer keeps `depth` dumps in flight."""
+    """The asyncio pipeline (Resource / JobQueue / async_wait_for_events): every task resolves to
+    the flags of its own dump while the producer keeps `depth` dumps in flight."""
     import asyncio
 
     from katsdpsigproc_b200 import resource, streaming
@@ -385,12 +385,12 @@ def test_async_streaming_flagger(context, abs_mode, depth):
                                                  threshold_args={"n_sigma": 9.0})
         assert stream.depth == depth
         jobs = resource.JobQueue()
-        results = []
+        results = [None] * len(dumps)
 
-        async def consume(task):
-            results.append((await task).copy())
-        for vis in dumps:
-            jobs.add(consume(stream.submit(vis)))
+        async def consume(index, task):            # tasks of different buffer sets may finish in any order
+            results[index] = (await task).copy()
+        for index, vis in enumerate(dumps):
+            jobs.add(consume(index, stream.submit(vis)))
             await jobs.finish(max_remaining=depth - 1)
         await jobs.finish()
         with pytest.raises(TypeError):
