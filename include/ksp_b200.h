@@ -48,7 +48,8 @@ extern "C" {
 #define KSP_FLAGS_CHANNEL 1
 #define KSP_FLAGS_FULL 2
 
-#define KSP_MAX_WINDOWS 7    /* sum-threshold window sizes 1 .. 2^(n-1) = 64 */
+#define KSP_MAX_WINDOWS 11   /* sum-threshold window sizes 1 .. 2^(n-1): up to 64 (n <= 7) on the
+                              * fast kernel, 128 .. 1024 on a general one */
 #define KSP_MAX_WIDTH 63     /* median filter width (odd) */
 
 int ksp_abi_version(void);

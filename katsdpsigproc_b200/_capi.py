@@ -15,7 +15,7 @@ from typing import Optional
 ABS_NUMPY = 0
 ABS_HYPOT = 1
 FLAGS_NONE, FLAGS_CHANNEL, FLAGS_FULL = 0, 1, 2
-MAX_WINDOWS = 7
+MAX_WINDOWS = 11
 MAX_WIDTH = 63
 H2D, D2H, D2D = 1, 2, 3
 

@@ -611,6 +611,153 @@ expand_flags_kernel(const uint32_t *__restrict__ bits_t, uint8_t *__restrict__ f
     }
 }
 
+// ---------------------------------------------------------------- more than 7 window sizes
+// The kernel above is built around a reach of two runs (windows up to 64).  Window sizes 128 ..
+// 1024 (n_windows 8 .. 11) take this plain statement of the contract instead: a block stages a
+// chunk of 8192 channels of one row (chunks overlap by the reach of all the sizes together, so
+// they are independent), keeps u = flagged ? 0 : x and the flag counts as doubling trees in
+// shared memory (one more level per window size while nothing new is flagged, a rebuild after a
+// size that flagged something) and dilates firing windows with a doubling OR.
+constexpr int TG_CH = 8192;
+constexpr int TG_THREADS = 1024;
+constexpr int TG_MAX_WINDOWS = KSP_MAX_WINDOWS;
+
+struct TgArgs {
+    const float *dev_t;
+    const float *noise;
+    uint8_t *flags_t;
+    uint32_t *bits_t;
+    int64_t channels, baselines, dev_stride, out_stride;
+    int n_windows, flag_value, edge, valid;
+    double n_sigma;
+    double scales[TG_MAX_WINDOWS];
+};
+
+__global__ void __launch_bounds__(TG_THREADS, 1)
+threshold_sum_general_kernel(const TgArgs a)
+{
+    extern __shared__ __align__(16) uint8_t tg_raw[];
+    float *x = reinterpret_cast<float *>(tg_raw);                 // TG_CH samples
+    float *ta = x + TG_CH, *tb = ta + TG_CH;                      // tree level, ping-pong
+    uint16_t *ca = reinterpret_cast<uint16_t *>(tb + TG_CH);      // flagged-sample counts, ping-pong
+    uint16_t *cb = ca + TG_CH;
+    uint8_t *fl = reinterpret_cast<uint8_t *>(cb + TG_CH);        // flags so far
+    uint8_t *ma = fl + TG_CH, *mb = ma + TG_CH;                   // firing starts -> covered samples
+    __shared__ float thr[TG_MAX_WINDOWS];
+
+    const int tid = threadIdx.x;
+    const int64_t row = blockIdx.x;
+    const int C = (int) a.channels;
+    const int base = (int) blockIdx.y * a.valid - a.edge;        // row channel of slot 0
+    const float *src = a.dev_t + row * a.dev_stride;
+    if (tid < a.n_windows)
+        thr[tid] = __double2float_rn((a.n_sigma * (double) a.noise[row]) * a.scales[tid]);
+    for (int i = tid; i < TG_CH; i += TG_THREADS) {
+        const int g = base + i;
+        x[i] = (g >= 0 && g < C) ? src[g] : 0.0f;
+        fl[i] = 0;
+    }
+    __syncthreads();
+
+    bool tree_ok = false;                                         // ta / ca hold level w - 1 of the current flags
+    for (int w = 0; w < a.n_windows; w++) {
+        const int win = 1 << w;
+        if (win > C) break;
+        if (!tree_ok || w == 0) {
+            for (int i = tid; i < TG_CH; i += TG_THREADS) {
+                ta[i] = fl[i] ? 0.0f : x[i];
+                ca[i] = fl[i];
+            }
+            __syncthreads();
+            for (int step = 1; step < win; step <<= 1) {
+                for (int i = tid; i < TG_CH; i += TG_THREADS) {
+                    const bool in = i + step < TG_CH;
+                    tb[i] = ta[i] + (in ? ta[i + step] : 0.0f);
+                    cb[i] = (uint16_t) (ca[i] + (in ? ca[i + step] : 0));
+                }
+                __syncthreads();
+                float *tf = ta; ta = tb; tb = tf;
+                uint16_t *cf = ca; ca = cb; cb = cf;
+            }
+        } else {
+            const int step = win >> 1;
+            for (int i = tid; i < TG_CH; i += TG_THREADS) {
+                const bool in = i + step < TG_CH;
+                tb[i] = ta[i] + (in ? ta[i + step] : 0.0f);
+                cb[i] = (uint16_t) (ca[i] + (in ? ca[i + step] : 0));
+            }
+            __syncthreads();
+            float *tf = ta; ta = tb; tb = tf;
+            uint16_t *cf = ca; ca = cb; cb = cf;
+        }
+        // windows that lie inside the band and inside the chunk
+        const double tw = (double) thr[w];
+        bool any = false;
+        for (int i = tid; i < TG_CH; i += TG_THREADS) {
+            const int g = base + i;
+            bool fire = false;
+            if (g >= 0 && g + win <= C && i + win <= TG_CH)
+                fire = (double) ta[i] > tw * (double) (win - (int) ca[i]);
+            ma[i] = fire ? 1 : 0;
+            any |= fire;
+        }
+        tree_ok = !__syncthreads_or(any);
+        if (!tree_ok) {
+            // covered[j] = OR of fire[j - k], k < win: doubling OR towards higher indices
+            for (int step = 1; step < win; step <<= 1) {
+                for (int i = tid; i < TG_CH; i += TG_THREADS) mb[i] = ma[i] | (i >= step ? ma[i - step] : 0);
+                __syncthreads();
+                uint8_t *mf = ma; ma = mb; mb = mf;
+            }
+            for (int i = tid; i < TG_CH; i += TG_THREADS) fl[i] |= ma[i];
+            __syncthreads();
+        }
+    }
+
+    // ---- the chunk's own part of the row
+    const int out_lo = (int) blockIdx.y * a.valid;
+    const int out_hi = min(C, out_lo + a.valid);
+    if (a.bits_t) {
+        for (int wd = tid; wd < a.valid / 32; wd += TG_THREADS) {
+            const int g0 = out_lo + 32 * wd;
+            if (g0 >= out_hi) break;
+            uint32_t bits = 0;
+            for (int j = 0; j < 32; j++)
+                if (g0 + j < out_hi && fl[g0 + j - base]) bits |= 1u << j;
+            a.bits_t[row * a.out_stride + (g0 >> 5)] = bits;
+        }
+    } else {
+        for (int g = out_lo + tid; g < out_hi; g += TG_THREADS)
+            a.flags_t[row * a.out_stride + g] = fl[g - base] ? (uint8_t) a.flag_value : (uint8_t) 0;
+    }
+}
+
+int launch_threshold_sum_general(cudaStream_t s, const float *dev_t, const float *noise,
+                                 uint8_t *flags_t, uint32_t *bits_t, int64_t channels,
+                                 int64_t baselines, int64_t dev_stride, int64_t out_stride,
+                                 int n_windows, double n_sigma, const double *scales, int flag_value)
+{
+    TgArgs a;
+    a.dev_t = dev_t; a.noise = noise; a.flags_t = flags_t; a.bits_t = bits_t;
+    a.channels = channels; a.baselines = baselines;
+    a.dev_stride = dev_stride; a.out_stride = out_stride;
+    a.n_windows = n_windows; a.flag_value = flag_value; a.n_sigma = n_sigma;
+    for (int w = 0; w < TG_MAX_WINDOWS; w++) a.scales[w] = w < n_windows ? scales[w] : 0.0;
+    const int reach = (1 << n_windows) - n_windows - 1;            // influence radius of a sample
+    a.edge = (int) (ksp_divup(reach, RUN) * RUN);
+    a.valid = TG_CH - 2 * a.edge;
+    if (a.valid < RUN) return KSP_ETOOLARGE;
+    const int64_t n_chunks = ksp_divup(channels, a.valid);
+    if (n_chunks > 65535) return KSP_ETOOLARGE;
+    const size_t smem = (size_t) TG_CH * (3 * sizeof(float) + 2 * sizeof(uint16_t) + 3);
+    KSP_CUDA(cudaFuncSetAttribute(threshold_sum_general_kernel,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+    dim3 grid((unsigned) baselines, (unsigned) n_chunks);
+    threshold_sum_general_kernel<<<grid, TG_THREADS, smem, s>>>(a);
+    KSP_CHECK_LAUNCH();
+    return 0;
+}
+
 size_t ts_smem_bytes(int threads, int buffers)
 {
     // span buffer(s), 7 words of state per run, thresholds and mbarriers, + 1 KB so that the
@@ -642,11 +789,15 @@ int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise,
 {
     if (channels < 0 || baselines < 0 || dev_stride < channels) return KSP_EINVAL;
     if (n_windows < 1 || !scales) return KSP_EINVAL;
-    if (n_windows > TS_MAX_WINDOWS) return KSP_ETOOLARGE;
+    if (n_windows > TG_MAX_WINDOWS) return KSP_ETOOLARGE;
     if (channels > 0x7fff0000) return KSP_ETOOLARGE;
     if (channels == 0 || baselines == 0) return 0;
     if (!dev_t || !noise || (!flags_t && !bits_t)) return KSP_EINVAL;
     if (baselines > 0x7fffffff) return KSP_ETOOLARGE;
+    if (n_windows > TS_MAX_WINDOWS)
+        return launch_threshold_sum_general(s, dev_t, noise, flags_t, bits_t, channels, baselines,
+                                            dev_stride, out_stride, n_windows, n_sigma, scales,
+                                            flag_value);
 
     TsArgs a;
     a.dev_t = dev_t; a.noise = noise; a.flags_t = flags_t; a.bits_t = bits_t;

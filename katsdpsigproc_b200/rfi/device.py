@@ -403,7 +403,8 @@ class ThresholdSimpleDevice(AbstractThresholdDevice):
 class ThresholdSumDeviceTemplate(FixedTuning, AbstractThresholdDeviceTemplate):
     """Offringa SumThreshold along channels with windows 1, 2, ..., 2^(n_windows-1).
 
-    Takes transposed (baseline-major) data.  ``n_windows`` is at most 7.
+    Takes transposed (baseline-major) data.  ``n_windows`` is at most 11 (windows up to 1024);
+    up to 7 (windows up to 64) run on the fast kernel.
     """
 
     transposed = True

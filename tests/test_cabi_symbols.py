@@ -55,5 +55,7 @@ def test_argument_errors_need_no_gpu():
 
 
 def test_struct_layout_matches_header():
-    # int64 x5, int x6, double, double[7], int64
-    assert ctypes.sizeof(_capi.FlaggerParams) == 5 * 8 + 6 * 4 + 8 + 7 * 8 + 8
+    # int64 x5, int x6, double, double[KSP_MAX_WINDOWS], int64
+    assert ctypes.sizeof(_capi.FlaggerParams) == 5 * 8 + 6 * 4 + 8 + _capi.MAX_WINDOWS * 8 + 8
+    header = open(HEADER).read()
+    assert f"#define KSP_MAX_WINDOWS {_capi.MAX_WINDOWS} " in header

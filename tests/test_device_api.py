@@ -77,9 +77,10 @@ def test_noise_templates(context, queue):
 
 def test_threshold_templates(context, queue):
     with pytest.raises(ValueError):
-        rfi.ThresholdSumDeviceTemplate(context, n_windows=8)
+        rfi.ThresholdSumDeviceTemplate(context, n_windows=12)
     with pytest.raises(ValueError):
         rfi.ThresholdSumDeviceTemplate(context, n_windows=0)
+    assert rfi.ThresholdSumDeviceTemplate(context, n_windows=11).n_windows == 11
     template = rfi.ThresholdSumDeviceTemplate(context, n_windows=3, flag_value=5)
     assert template.transposed
     op = template.instantiate(queue, 117, 273, 11.0, threshold_falloff=1.5)

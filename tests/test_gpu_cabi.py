@@ -242,6 +242,42 @@ def test_threshold_sum_many_tiles_per_block(channels, baselines):
     check_sum(dev, noise, 3.5, 7, 1.2)
 
 
+@pytest.mark.parametrize("n_windows", [8, 9, 10, 11])
+@pytest.mark.parametrize("channels", [700, 8192, 20000])
+def test_threshold_sum_many_windows(n_windows, channels):
+    """Window sizes beyond 64 (n_windows 8..11) take the general kernel: broad interference of
+    every width, chunk seams, rows shorter than the largest window."""
+    rs = np.random.RandomState(n_windows * 1000 + channels)
+    baselines = 6
+    dev = rs.standard_normal((channels, baselines)).astype(np.float32)
+    for bl in range(baselines):
+        for _ in range(4 + channels // 1500):
+            width = int(rs.choice([1, 3, 20, 90, 200, 400, 900]))
+            width = min(width, channels // 2)
+            s = rs.randint(0, channels - width)
+            dev[s:s + width, bl] += rs.uniform(0.4, 5.0)
+    dev[rs.random_sample(dev.shape) < 1 / 128] += 30.0
+    noise = rs.uniform(0.8, 1.2, baselines).astype(np.float32)
+    noise[5] = np.nan
+    check_sum(dev, noise, 3.0, n_windows, 1.2, flag_value=2)
+    check_sum(dev, noise, 2.5, n_windows, 1.5, pad=4)
+
+
+def test_flagger_fused_many_windows(abs_mode):
+    rs = np.random.RandomState(12)
+    channels, baselines = 9000, 40
+    vis = complex_normal(rs, (channels, baselines))
+    for _ in range(60):
+        bl, width = rs.randint(0, baselines), int(rs.choice([5, 60, 300, 700]))
+        s = rs.randint(0, channels - width)
+        vis[s:s + width, bl] += rs.uniform(0.5, 3.0)
+    flags, dev, noise = contract.flagger(vis, None, n_windows=10, n_sigma=4.0, abs_mode=abs_mode)
+    out_flags, out_noise = cu.flagger(vis, None, n_windows=10, n_sigma=4.0, abs_mode=abs_mode)
+    assert_same_f32(noise, out_noise)
+    np.testing.assert_array_equal(flags, out_flags)
+    assert flags.any()
+
+
 def test_threshold_sum_nan_noise_and_ties():
     dev = np.ones((64, 3), np.float32)
     noise = np.array([np.nan, 1.0 / 11.0, -1.0], np.float32)
