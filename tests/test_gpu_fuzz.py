@@ -63,6 +63,38 @@ def test_fused_flagger_fuzz(abs_mode, seed):
     np.testing.assert_array_equal(want_flags, flags, err_msg=f"seed {seed}")
 
 
+@pytest.mark.parametrize("seed", range(30))
+def test_fused_flagger_fuzz_other_parameters(abs_mode, seed):
+    """The same with median widths other than 13 (sliding-window and generic kernels) and up to
+    11 window sizes (general sum-threshold kernel), amplitude input now and then."""
+    rs = np.random.RandomState(5000 + seed)
+    channels = int(rs.choice([1, 9, 40, 129, 700, 2049, 4096 + 17, 9000]))
+    baselines = int(rs.choice([1, 3, 31, 33, 70]))
+    vis = random_vis(rs, channels, baselines)
+    width = int(rs.choice([1, 3, 5, 7, 9, 11, 15, 17, 21, 31, 33, 45]))
+    n_windows = int(rs.randint(1, 12))
+    n_sigma = float(rs.choice([2.0, 3.0, 4.5]))
+    falloff = float(rs.choice([1.2, 1.5]))
+    amplitudes = bool(seed % 5 == 0)
+    data = np.abs(vis) if amplitudes else vis
+    flag_kind = rs.randint(0, 3)
+    fl = None
+    if flag_kind == 1:
+        fl = (rs.random_sample(channels) < 0.1).astype(np.uint8)
+    elif flag_kind == 2:
+        fl = (rs.random_sample(vis.shape) < 0.05).astype(np.uint8) * 7
+    with np.errstate(all="ignore"):
+        want_flags, _, want_noise = contract.flagger(
+            data, fl, width=width, n_windows=n_windows, n_sigma=n_sigma, threshold_falloff=falloff,
+            flag_value=1, amplitudes=amplitudes, abs_mode=abs_mode)
+    flags, noise = cu.flagger(data, fl, width=width, n_windows=n_windows, n_sigma=n_sigma,
+                              falloff=falloff, flag_value=1, amplitudes=amplitudes,
+                              abs_mode=abs_mode, pad=int(rs.choice([0, 3])))
+    same = (noise.view(np.uint32) == want_noise.view(np.uint32)) | (np.isnan(noise) & np.isnan(want_noise))
+    assert same.all(), (seed, noise[~same][:4], want_noise[~same][:4])
+    np.testing.assert_array_equal(want_flags, flags, err_msg=f"seed {seed}")
+
+
 @pytest.mark.parametrize("seed", range(25))
 def test_threshold_sum_fuzz(seed):
     """Deviations with broad and clustered excesses close to the thresholds."""
