@@ -1,7 +1,7 @@
 """Streaming ingest around :class:`~katsdpsigproc_b200.rfi.device.FlaggerDevice`.
 
-The flagger itself needs ~1.6 ms per MeerKAT dump on a B200, moving the dump over
-PCIe takes ~45 ms, so an ingest loop is transfer-bound and must overlap the three
+The flagger itself needs ~1.2 ms per MeerKAT dump on a B200, moving the dump over
+PCIe takes ~40 ms, so an ingest loop is transfer-bound and must overlap the three
 legs: host -> device copy of dump *i+1*, flagging of dump *i*, device -> host copy
 of the flags of dump *i-1*.  This is the pattern the reference documents for its
 users (``doc/user/sync.rst``, ``doc/user/resource.rst``: one command queue per
