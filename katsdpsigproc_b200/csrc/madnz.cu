@@ -1066,6 +1066,9 @@ percentile5_stream_kernel(const void *__restrict__ src, float *__restrict__ dest
 constexpr int PF_THREADS = 256;
 constexpr int PF_FINE = 1024;                 // histogram bins per bracket: 32 coarse x 32
 constexpr int PF_UNROLL = 4;                  // 16-byte loads in flight per thread
+#ifndef PF_SAMPLE_VECS
+#define PF_SAMPLE_VECS 8                      // 16-byte sample loads per thread (4 or 8)
+#endif
 
 // fine bin / rank lookup in a 32 x 32 two-level histogram (lane owns coarse bin `lane`)
 __device__ __forceinline__ BinHit locate_rank32(const uint32_t *coarse, const uint32_t *fine,
@@ -1175,20 +1178,21 @@ percentile5_fast_kernel(const void *__restrict__ src, float *__restrict__ dest, 
     if (tid < 16) misc[tid] = (tid == 4) ? 0xffffffffu : 0u;
     const int n_vec = n / EPV;
     const float4 *row4 = reinterpret_cast<const float4 *>(row);
-    float4 sv[4];
+    float4 sv[PF_SAMPLE_VECS];
     {
-        const uint32_t step = (uint32_t) n_vec >> 10;
+        constexpr int LOG_N = 8 + (PF_SAMPLE_VECS == 8 ? 3 : 2);             // log2(sample vectors)
+        const uint32_t step = (uint32_t) n_vec >> LOG_N;
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
-            const uint32_t i = (uint32_t) tid * 4u + g;
-            uint32_t pos = (uint32_t) (((uint64_t) i * (uint32_t) n_vec) >> 10);
+        for (int g = 0; g < PF_SAMPLE_VECS; g++) {
+            const uint32_t i = (uint32_t) tid * PF_SAMPLE_VECS + g;
+            uint32_t pos = (uint32_t) (((uint64_t) i * (uint32_t) n_vec) >> LOG_N);
             pos += (((i * 2654435761u) >> 16) * step) >> 16;
             sv[g] = __ldg(row4 + min((int) pos, n_vec - 1));
         }
     }
     __syncthreads();
 #pragma unroll
-    for (int g = 0; g < 4; g++) {
+    for (int g = 0; g < PF_SAMPLE_VECS; g++) {
         float a[4];
         amplitudes(sv[g], a);
 #pragma unroll
@@ -1493,7 +1497,7 @@ extern "C" int ksp_percentile5(void *stream, const void *src, float *dest, int64
             return !(e && atoi(e) == 0);
         }();
         if (fast_allowed && aligned && n_cols >= 8192) {
-            const double m = 1024.0 * epv;                          // samples
+            const double m = 256.0 * PF_SAMPLE_VECS * epv;          // samples
             const double h = 4.5 * sqrt(0.25 / m);                  // bracket half-width (rank fraction)
             const double frac = 6.0 * h + 3.0 / 1024.0;             // kept: three brackets + bin interpolation slack
             const double per_t = (double) ksp_divup(n_cols, PF_THREADS);
