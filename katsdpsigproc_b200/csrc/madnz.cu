@@ -1080,7 +1080,7 @@ percentile5_stream_kernel(const void *__restrict__ src, float *__restrict__ dest
 // ------------------------------------------------------------------ Percentile5, fast path
 // The techniques of madnz_stream_kernel applied to three ranks at once, for rows that can be
 // read with aligned 16-byte loads (the usual case):
-//   1. 1024 x 16 bytes of the row are sampled (4096 amplitudes, or 2048 from complex input)
+//   1. 2048 x 16 bytes of the row are sampled (8192 amplitudes, or 4096 from complex input)
 //      into a two-level histogram over the float bit patterns; every warp locates the sample
 //      quantiles h either side of the 25 %, 50 % and 75 % ranks (h = 4.5 standard errors)
 //      and interpolates inside their bins: three disjoint brackets [lo_k, hi_k];
