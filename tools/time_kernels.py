@@ -115,6 +115,10 @@ def main():
         pct = torch.empty(5, B, dtype=torch.float32, device=dev)
         rec("percentile5_f32", timeit(lambda: _capi.call(
             "ksp_percentile5", S, p(dev_t), p(pct), B, CT, B, 0, C, 1, 0), args.reps, flush), 4)
+        # complex input: rows of the channel-major dump, as the reference's percentile script does
+        pct_c = torch.empty(5, C, dtype=torch.float32, device=dev)
+        rec("percentile5_c64", timeit(lambda: _capi.call(
+            "ksp_percentile5", S, p(vis), p(pct_c), C, B, C, 0, B, 0, 0), args.reps, flush), 8)
         mask = (torch.rand(C, device=dev) < 0.9).float()
         dest = torch.empty(B, 2, dtype=torch.float32, device=dev)
         rec("maskedsum_c64", timeit(lambda: _capi.call(
