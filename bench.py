@@ -221,10 +221,12 @@ def b200_arm(args) -> None:
     import torch
     import torch.distributed as dist
 
-    from katsdpsigproc_b200 import _capi, accel, cuda, streaming
+    from katsdpsigproc_b200 import _capi, accel, cuda, sharding, streaming
     from katsdpsigproc_b200.rfi import device as rfi_device
 
     torch.cuda.set_device(local_rank)
+    # one process per GPU: run (and allocate the pinned staging buffers) next to that GPU
+    bound_cpus = sharding.bind_to_device_locality(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -368,7 +370,9 @@ def b200_arm(args) -> None:
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e,
                     "how": "StreamingFlagger: pinned host -> device, flagger, flags -> pinned host; "
-                           "2 dumps in flight on upload/compute/download queues; wall clock"},
+                           "2 dumps in flight on upload/compute/download queues; wall clock",
+                    "cpu_binding": (f"rank 0 bound to {len(bound_cpus)} CPUs next to its GPU (NVML affinity)"
+                                    if bound_cpus else "none")},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "roofline": roofline,

@@ -76,3 +76,37 @@ def gather_flags(local_flags: Any, baselines: int, group: Optional[Any] = None, 
 
 def shard_sizes(baselines: int, world_size: int, align: int = 32) -> Sequence[int]:
     return [stop - start for start, stop in baseline_ranges(baselines, world_size, align)]
+
+
+def bind_to_device_locality(device_index: int) -> Optional[List[int]]:
+    """Pin the calling process to the CPUs that are closest to GPU ``device_index``.
+
+    With one process per GPU, the pinned staging buffers of
+    :class:`~katsdpsigproc_b200.streaming.StreamingFlagger` are then allocated (first touch)
+    on the NUMA node the GPU hangs off, and the PCIe copies of all ranks stop crossing the
+    socket interconnect - on an 8-GPU box that is the difference between the ranks sharing one
+    memory controller and each using its own.  Uses NVML (``nvidia-ml-py``); returns the CPU
+    list it bound to, or ``None`` if NVML or the affinity information is not available (the
+    process is then left as it was).
+    """
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        try:
+            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            words = -(-(os.cpu_count() or 1) // 64)
+            mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
+        finally:
+            pynvml.nvmlShutdown()
+        cpus = [64 * w + bit for w, word in enumerate(mask) for bit in range(64) if (word >> bit) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
