@@ -17,7 +17,8 @@
 int ksp_threshold_sum_packed(cudaStream_t s, const float *dev_t, const float *noise,
                              uint32_t *bits_t, int64_t channels, int64_t baselines,
                              int64_t dev_stride, int64_t words_stride, int n_windows,
-                             double n_sigma, const double *scales);
+                             double n_sigma, const double *scales, uint32_t *work);
+size_t ksp_threshold_work_bytes(int64_t channels, int64_t baselines);
 int ksp_expand_flags(cudaStream_t s, const uint32_t *bits_t, uint8_t *flags, int64_t channels,
                      int64_t baselines, int64_t words_stride, int64_t flags_stride, int flag_value);
 
@@ -27,7 +28,7 @@ struct Layout {
     int64_t chunk;        // baselines per chunk (multiple of 32)
     int64_t dev_stride;   // floats per baseline row of dev_t
     int64_t words_stride; // words per baseline row of bits_t
-    size_t dev_bytes, bits_bytes;   // per lane
+    size_t dev_bytes, bits_bytes, work_bytes;   // per lane
     int lanes;            // chunks in flight (1 = everything on the caller's stream)
 };
 
@@ -100,6 +101,7 @@ Layout make_layout(const ksp_flagger_params *p)
     l.chunk = chunk;
     l.dev_bytes = (size_t) chunk * (size_t) l.dev_stride * 4;
     l.bits_bytes = (size_t) chunk * (size_t) l.words_stride * 4;
+    l.work_bytes = (ksp_threshold_work_bytes(p->channels, chunk) + 1023) / 1024 * 1024;   // keeps every lane 1 KB aligned
     const int64_t n_chunks = ksp_divup(p->baselines, chunk);
     if (lanes > n_chunks) lanes = (int) n_chunks;
     if (ksp_profile_active()) lanes = 1;   // stage timing needs the stages one after another
@@ -113,7 +115,7 @@ extern "C" size_t ksp_flagger_scratch_bytes(const ksp_flagger_params *p)
 {
     if (!p || p->channels <= 0 || p->baselines <= 0) return 0;
     Layout l = make_layout(p);
-    return (l.dev_bytes + l.bits_bytes) * (size_t) l.lanes;
+    return (l.dev_bytes + l.bits_bytes + l.work_bytes) * (size_t) l.lanes;
 }
 
 extern "C" int64_t ksp_flagger_chunk_baselines(const ksp_flagger_params *p)
@@ -134,7 +136,7 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
     if (p->flag_mode != KSP_FLAGS_NONE && !input_flags) return KSP_EINVAL;
     if (p->flags_stride < p->baselines || p->vis_stride < p->baselines) return KSP_EINVAL;
     Layout l = make_layout(p);
-    const size_t lane_bytes = l.dev_bytes + l.bits_bytes;
+    const size_t lane_bytes = l.dev_bytes + l.bits_bytes + l.work_bytes;
     if (scratch_bytes < lane_bytes * (size_t) l.lanes) return KSP_ESCRATCH;
     if ((uintptr_t) scratch % 16) return KSP_EALIGN;
     cudaStream_t user = (cudaStream_t) stream;
@@ -157,6 +159,7 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
         cudaStream_t s = pool ? pool->stream[lane] : user;
         float *dev_t = (float *) ((char *) scratch + lane_bytes * (size_t) lane);
         uint32_t *bits_t = (uint32_t *) ((char *) dev_t + l.dev_bytes);
+        uint32_t *work = (uint32_t *) ((char *) bits_t + l.bits_bytes);
         const int64_t nb = (p->baselines - b0 < l.chunk) ? p->baselines - b0 : l.chunk;
         const void *vis_c = (const char *) vis + (size_t) b0 * vis_elem;
         const uint8_t *in_fl = input_flags;
@@ -174,7 +177,7 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
         if (rc) return rc;
         ksp_profile_begin(KSP_STAGE_THRESHOLD, s);
         rc = ksp_threshold_sum_packed(s, dev_t, noise + b0, bits_t, p->channels, nb, l.dev_stride,
-                                      l.words_stride, p->n_windows, p->n_sigma, p->scales);
+                                      l.words_stride, p->n_windows, p->n_sigma, p->scales, work);
         ksp_profile_end(KSP_STAGE_THRESHOLD, s);
         if (rc) return rc;
         ksp_profile_begin(KSP_STAGE_EXPAND, s);

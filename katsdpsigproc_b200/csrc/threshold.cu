@@ -72,6 +72,7 @@ struct TsArgs {
     int use_tma;           // stage the span with one TMA tile load (needs tmap)
     int two_buffers;       // with TMA: second span buffer, the next tile loads while this one is worked on
     int n_chunks;          // spans per row
+    uint32_t *work;        // two-pass mode: work[0] = number of listed tiles, work[1..] = their ids
     int chunk_valid;       // channels produced per block (multiple of 32)
     int edge;              // halo on each side of a span (multiple of 32; 0 when one block per row)
     double n_sigma;
@@ -185,8 +186,17 @@ __device__ __noinline__ uint32_t window_candidates(const float *rowbuf, int r, u
 #ifndef TS_MIN_BLOCKS
 #define TS_MIN_BLOCKS 4
 #endif
-template <bool PACKED, int TFIX>
-__global__ void __launch_bounds__(TFIX ? TFIX : TS_MAX_THREADS, TFIX ? TS_MIN_BLOCKS : 4)
+// MODE 0: everything in one kernel.  Two-pass mode (fused flagger): MODE 1 does window size 1 and
+// the vote for every tile - the whole job for almost all of them - and lists the few tiles where
+// some larger window might fire; MODE 2 then runs the full algorithm over the listed tiles.  The
+// first pass carries none of the rare paths, needs half the registers and runs with more blocks
+// per SM.
+#ifndef TS_LEAN_BLOCKS
+#define TS_LEAN_BLOCKS 7
+#endif
+template <bool PACKED, int TFIX, int MODE>
+__global__ void __launch_bounds__(TFIX ? TFIX : TS_MAX_THREADS,
+                                  MODE == 1 ? TS_LEAN_BLOCKS : (TFIX ? TS_MIN_BLOCKS : 4))
 threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
 {
     extern __shared__ __align__(1024) uint8_t sm_raw[];
@@ -233,31 +243,41 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
         mbar_expect_tx(&mbar[buf], (uint32_t) span * 4u);
         tma_load_3d(buf ? rowbuf1 : rowbuf0, &tmap, 0, (y * a.chunk_valid - a.edge) >> 5, (int) r, &mbar[buf]);
     };
-    // tile -> (row, span) without a division per tile: step both by the grid size
+    // tiles of this block: MODE 2 takes them from the list of the first pass, the others walk all
+    // (row, span) pairs without a division per tile, stepping both by the grid size
+    const int64_t n_iter = (MODE == 2) ? (int64_t) a.work[0] : total;
+    auto listed = [&](int64_t i, int64_t &r, int &y) {
+        const uint32_t t = a.work[1 + i];
+        r = t / (uint32_t) a.n_chunks;
+        y = (int) (t - (uint32_t) r * (uint32_t) a.n_chunks);
+    };
     int64_t row = (int64_t) blockIdx.x / a.n_chunks;
     int span_y = (int) ((int64_t) blockIdx.x - row * a.n_chunks);
+    if (MODE == 2 && (int64_t) blockIdx.x < n_iter) listed(blockIdx.x, row, span_y);
     const int64_t step_rows = (int64_t) gridDim.x / a.n_chunks;
     const int step_y = (int) ((int64_t) gridDim.x - step_rows * a.n_chunks);
     // the noise of a tile's row is fetched one tile ahead, like its samples
     float noise_now = 0.0f;
-    if (tid < a.n_windows && (int64_t) blockIdx.x < total) noise_now = a.noise[row];
-    if (a.use_tma && a.two_buffers && tid == 0 && (int64_t) blockIdx.x < total) issue_tile(row, span_y, 0);
+    if (tid < a.n_windows && (int64_t) blockIdx.x < n_iter) noise_now = a.noise[row];
+    if (a.use_tma && a.two_buffers && tid == 0 && (int64_t) blockIdx.x < n_iter) issue_tile(row, span_y, 0);
 
     // ---- persistent loop over tiles; with two buffers the next tile's load is in flight while
     //      this one is processed
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile < total; tile += gridDim.x, it++) {
+    for (int64_t tile = blockIdx.x; tile < n_iter; tile += gridDim.x, it++) {
     const int buf = a.two_buffers ? (it & 1) : 0;
     float *rowbuf = buf ? rowbuf1 : rowbuf0;
     const int base = span_y * a.chunk_valid - a.edge;             // row channel of slot 0
     const float *src = a.dev_t + row * a.dev_stride;
+    const bool has_next = tile + gridDim.x < n_iter;
     int64_t next_row = row + step_rows;
     int next_y = span_y + step_y;
-    if (next_y >= a.n_chunks) {
+    if (MODE == 2) {
+        if (has_next) listed(tile + gridDim.x, next_row, next_y);
+    } else if (next_y >= a.n_chunks) {
         next_y -= a.n_chunks;
         next_row++;
     }
-    const bool has_next = tile + gridDim.x < total;
 
     // (everybody has left the previous tile's last barrier: thr, Fsm, stat and the other buffer
     // are free)
@@ -424,7 +444,13 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
         any |= !(reach_max <= lim_small);
         if (!__syncthreads_or(any)) goto write_out;
     }
+    if (MODE == 1) {
+        // first pass: leave the tile to the second pass (its flags are not written here)
+        if (tid == 0) a.work[1 + atomicAdd(&a.work[0], 1u)] = (uint32_t) (row * a.n_chunks + span_y);
+        goto next_tile;
+    }
 
+    if (MODE != 1)
     for (int w = 1; w < a.n_windows; w++) {
         const int win = 1 << w;
         if (win > C) break;
@@ -481,6 +507,7 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
     }
 
 write_out:
+    {
     // ---- write my 32 flags if my run belongs to this block's output range
     const int64_t out_lo = (int64_t) span_y * a.chunk_valid;
     const int64_t out_hi = min((int64_t) C, out_lo + (int64_t) a.chunk_valid);
@@ -509,6 +536,8 @@ write_out:
             }
         }
     }
+    }
+next_tile:
     row = next_row;
     span_y = next_y;
     }   // tiles
@@ -768,6 +797,18 @@ size_t ts_smem_bytes(int threads, int buffers)
 
 // Blocks of the persistent grid: as many as fit on the device at once.
 template <typename Kernel>
+int ts_blocks(Kernel kernel, const TsArgs &a, int threads, size_t smem, int64_t *blocks)
+{
+    int per_sm = 0;
+    KSP_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t total = a.baselines * (int64_t) a.n_chunks;
+    *blocks = (int64_t) per_sm * ksp_sm_count();
+    if (*blocks > total) *blocks = total;
+    return 0;
+}
+
+template <typename Kernel>
 int ts_launch(Kernel kernel, cudaStream_t s, const TsArgs &a, const CUtensorMap &tmap, int threads,
               size_t smem)
 {
@@ -785,7 +826,7 @@ int ts_launch(Kernel kernel, cudaStream_t s, const TsArgs &a, const CUtensorMap 
 int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise, uint8_t *flags_t,
                          uint32_t *bits_t, int64_t channels, int64_t baselines, int64_t dev_stride,
                          int64_t out_stride, int n_windows, double n_sigma, const double *scales,
-                         int flag_value)
+                         int flag_value, uint32_t *work = nullptr)
 {
     if (channels < 0 || baselines < 0 || dev_stride < channels) return KSP_EINVAL;
     if (n_windows < 1 || !scales) return KSP_EINVAL;
@@ -859,12 +900,33 @@ int launch_threshold_sum(cudaStream_t s, const float *dev_t, const float *noise,
     a.two_buffers = (a.use_tma && ts_smem_bytes(threads, 2) <= 48 * 1024 &&
                      baselines * (int64_t) n_chunks > 1) ? 1 : 0;
     const size_t smem = ts_smem_bytes(threads, a.two_buffers ? 2 : 1);
+    a.work = nullptr;
     if (bits_t) {
-        if (threads == 128) return ts_launch(threshold_sum_kernel<true, 128>, s, a, tmap, threads, smem);
-        return ts_launch(threshold_sum_kernel<true, 0>, s, a, tmap, threads, smem);
+        if (threads == 128 && work && a.two_buffers && baselines * (int64_t) n_chunks < 0x7fffffff) {
+            // two passes (see the kernel): lean first pass over every tile, full algorithm over
+            // the tiles it lists
+            static const bool two_pass = [] {
+                const char *e = getenv("KSP_TS_TWO_PASS");
+                return !(e && atoi(e) == 0);
+            }();
+            if (two_pass) {
+                a.work = work;
+                KSP_CUDA(cudaMemsetAsync(work, 0, sizeof(uint32_t), s));
+                // the first pass runs single-buffered: with its small footprint (56 registers,
+                // 21 KB) nine blocks share an SM and hide each other's tile loads
+                TsArgs a1 = a;
+                a1.two_buffers = 0;
+                int rc = ts_launch(threshold_sum_kernel<true, 128, 1>, s, a1, tmap, threads,
+                                   ts_smem_bytes(threads, 1));
+                if (rc) return rc;
+                return ts_launch(threshold_sum_kernel<true, 128, 2>, s, a, tmap, threads, smem);
+            }
+        }
+        if (threads == 128) return ts_launch(threshold_sum_kernel<true, 128, 0>, s, a, tmap, threads, smem);
+        return ts_launch(threshold_sum_kernel<true, 0, 0>, s, a, tmap, threads, smem);
     }
-    if (threads == 128) return ts_launch(threshold_sum_kernel<false, 128>, s, a, tmap, threads, smem);
-    return ts_launch(threshold_sum_kernel<false, 0>, s, a, tmap, threads, smem);
+    if (threads == 128) return ts_launch(threshold_sum_kernel<false, 128, 0>, s, a, tmap, threads, smem);
+    return ts_launch(threshold_sum_kernel<false, 0, 0>, s, a, tmap, threads, smem);
 }
 
 }  // namespace
@@ -881,14 +943,22 @@ extern "C" int ksp_threshold_sum(void *stream, const float *dev_t, const float *
 }
 
 // internal (fused flagger): bit-packed output, words_stride words per baseline row
+// work: optional scratch of ksp_threshold_work_bytes() bytes for the two-pass mode
 int ksp_threshold_sum_packed(cudaStream_t s, const float *dev_t, const float *noise,
                              uint32_t *bits_t, int64_t channels, int64_t baselines,
                              int64_t dev_stride, int64_t words_stride, int n_windows,
-                             double n_sigma, const double *scales)
+                             double n_sigma, const double *scales, uint32_t *work)
 {
     if (words_stride < ksp_divup(channels, 32)) return KSP_EINVAL;
     return launch_threshold_sum(s, dev_t, noise, nullptr, bits_t, channels, baselines, dev_stride,
-                                words_stride, n_windows, n_sigma, scales, 1);
+                                words_stride, n_windows, n_sigma, scales, 1, work);
+}
+
+// upper bound on the tile list of the two-pass mode: one word per (baseline, span) + the count
+size_t ksp_threshold_work_bytes(int64_t channels, int64_t baselines)
+{
+    const int64_t spans = channels / 2048 + 2;              // spans hold at least 2048 own channels
+    return (size_t) (baselines * spans + 1) * sizeof(uint32_t);
 }
 
 int ksp_expand_flags(cudaStream_t s, const uint32_t *bits_t, uint8_t *flags, int64_t channels,
