@@ -199,6 +199,7 @@ __global__ void __launch_bounds__(TFIX ? TFIX : TS_MAX_THREADS,
                                   MODE == 1 ? TS_LEAN_BLOCKS : (TFIX ? TS_MIN_BLOCKS : 4))
 threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
 {
+    if (MODE == 2 && blockIdx.x >= a.work[0]) return;           // nothing listed for this block
     extern __shared__ __align__(1024) uint8_t sm_raw[];
     // the swizzle pattern is a function of the shared-memory address: align the span to 1 KB
     float *sm = reinterpret_cast<float *>(sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u));
