@@ -38,6 +38,7 @@ extern "C" {
 #define KSP_ESCRATCH (-4)    /* scratch buffer too small */
 #define KSP_ENOJIT (-5)      /* the run-time compiler (NVRTC) is not available */
 #define KSP_EJIT (-6)        /* run-time compilation failed: see ksp_jit_log() */
+#define KSP_ETIMEOUT (-7)    /* the dataflow flagger abandoned a launch (see ksp_flagger_stats) */
 
 /* complex64 amplitude rule: which host np.abs the result equals */
 #define KSP_ABS_NUMPY 0      /* numpy on AVX-512F hosts: L*sqrt(fma(r,r,1)), r = min/max */
@@ -170,10 +171,17 @@ int ksp_maskedsum(void *stream, const void *src, const float *mask, void *dest, 
 
 /* ------------------------------------------------------------------------
  * Fused flagger: the standard median + MAD + SumThreshold combination of
- * rfi/device.py:1111-1166 in four launches per baseline chunk (background
- * written baseline-major, noise, thresholds with bit-packed flags, expansion to
- * channel-major bytes).  Several chunks are in flight on internal streams that
- * fork from / join into `stream`; the scratch holds every chunk in flight.
+ * rfi/device.py:1111-1166 (5 launches, 31 B/vis of memory traffic in the reference).
+ *
+ * Dataflow form (width 13, up to 7 window sizes, channels a multiple of 32; the default from
+ * 2048 channels): ONE persistent kernel per dump.  Background tiles, noise rows, threshold
+ * spans and bit -> byte expansion tiles are work items of one schedule; the deviations pass
+ * from item to item through a ring of a few strips of 32 baselines that stays in the L2 cache,
+ * so device memory sees the visibilities once and the flags once.
+ *
+ * Chunked form (everything else, or chunk_baselines > 0): four launches per chunk of
+ * baselines, several chunks in flight on internal streams that fork from / join into `stream`.
+ * The scratch holds the ring, or every chunk in flight.
  * ---------------------------------------------------------------------- */
 typedef struct ksp_flagger_params {
     int64_t channels, baselines;
@@ -184,11 +192,13 @@ typedef struct ksp_flagger_params {
     int is_amplitude;
     int flag_mode;               /* KSP_FLAGS_* */
     int abs_mode;                /* KSP_ABS_* */
-    int n_windows;               /* 0 = simple threshold */
+    int n_windows;               /* sum-threshold window sizes 1 .. 2^(n_windows-1); >= 1 */
     int flag_value;
     double n_sigma;
     double scales[KSP_MAX_WINDOWS];
-    int64_t chunk_baselines;     /* 0 = one chunk per lane (KSP_LANES, default 4; KSP_CHUNK overrides) */
+    int64_t chunk_baselines;     /* 0 = library's choice (dataflow form where it applies, else one chunk
+                                  * per lane: KSP_LANES, default 4; KSP_CHUNK); > 0 = chunked form with
+                                  * this chunk; < 0 = dataflow form or KSP_EINVAL */
 } ksp_flagger_params;
 
 size_t ksp_flagger_scratch_bytes(const ksp_flagger_params *p);
@@ -197,6 +207,20 @@ int64_t ksp_flagger_chunk_baselines(const ksp_flagger_params *p);
 int ksp_flagger(void *stream, const ksp_flagger_params *p, const void *vis,
                 const uint8_t *input_flags, float *noise, uint8_t *flags, void *scratch,
                 size_t scratch_bytes);
+
+/* Diagnostics of the last ksp_flagger call that used `scratch` (waits for `stream`).  Dataflow
+ * form: SM cycles spent per kind of work item summed over all blocks, cycles spent waiting for
+ * other items, items run, noise rows that fell back to the radix select, and whether the launch
+ * was abandoned (a wait exceeded its limit: returns KSP_ETIMEOUT, results are invalid).
+ * Chunked form: zeros.  out[i] for i < n, indices KSP_DF_STAT_*. */
+#define KSP_DF_STATS 8
+enum { KSP_DF_STAT_CYCLES_BG = 0, KSP_DF_STAT_CYCLES_NOISE, KSP_DF_STAT_CYCLES_THRESHOLD,
+       KSP_DF_STAT_CYCLES_EXPAND, KSP_DF_STAT_CYCLES_WAIT, KSP_DF_STAT_ITEMS,
+       KSP_DF_STAT_FALLBACKS, KSP_DF_STAT_ERROR };
+int ksp_flagger_stats(void *stream, const ksp_flagger_params *p, const void *scratch,
+                      unsigned long long *out, int n);
+/* 1 if ksp_flagger runs these parameters in the dataflow form, else 0 */
+int ksp_flagger_is_dataflow(const ksp_flagger_params *p);
 
 /* ------------------------------------------------------------------------
  * General-purpose operations that sit beside the RFI ones in the reference.

@@ -137,6 +137,9 @@ PROTOTYPES = {
         [c_void_p, POINTER(FlaggerParams), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
          c_size_t],
     ),
+    "ksp_flagger_stats": (
+        c_int, [c_void_p, POINTER(FlaggerParams), c_void_p, POINTER(ctypes.c_ulonglong), c_int]),
+    "ksp_flagger_is_dataflow": (c_int, [POINTER(FlaggerParams)]),
 }
 
 _lib: Optional[ctypes.CDLL] = None
@@ -182,6 +185,11 @@ def kernel_launch_count() -> int:
 
 
 STAGE_NAMES = ("background", "noise", "threshold", "expand_flags")
+
+
+# indices of ksp_flagger_stats (KSP_DF_STAT_*)
+DF_STAT_NAMES = ("cycles_background", "cycles_noise", "cycles_threshold", "cycles_expand",
+                 "cycles_wait", "items", "fallbacks", "error")
 
 
 def profile_enable(on: bool) -> None:

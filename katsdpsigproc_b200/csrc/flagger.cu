@@ -1,6 +1,7 @@
 // Fused flagger: the standard median + MAD + SumThreshold combination of
-// reference rfi/device.py:1111-1166 (5 launches, 31 B/vis of HBM traffic) as
-// 4 launches per CHUNK of baselines:
+// reference rfi/device.py:1111-1166 (5 launches, 31 B/vis of HBM traffic).  Two forms: the
+// dataflow kernel of dataflow.cu (one persistent launch per dump, the default where it applies)
+// and, in this file, the chunked form, 4 launches per CHUNK of baselines:
 //
 //   vis[:, chunk] --bg13_kernel--> dev_t (chunk x C float32, scratch)
 //                 --madnz_stream_kernel--> noise[chunk]
@@ -12,6 +13,7 @@
 // run on separate internal streams ("lanes", each with its own scratch) that fork
 // from and join into the caller's stream, so kernel tails overlap.
 #include "common.cuh"
+#include "dataflow.h"
 #include <stdlib.h>
 
 int ksp_threshold_sum_packed(cudaStream_t s, const float *dev_t, const float *noise,
@@ -71,14 +73,21 @@ Layout make_layout(const ksp_flagger_params *p)
     // Measured on B200 (profiles/): the stages are issue-bound rather than HBM-bound and launches
     // cost ~9 us each, so few large chunks beat many L2-sized ones (KSP_CHUNK / chunk_baselines
     // override the default below).
-    const char *e = getenv("KSP_LANES");
-    int lanes = e ? atoi(e) : 4;
-    if (lanes < 1) lanes = 1;
-    if (lanes > MAX_LANES) lanes = MAX_LANES;
+    // (the environment is read ONCE per process: the scratch size, queried when the operation is
+    // instantiated, and every later launch must see the same layout)
+    static const int env_lanes = [] {
+        const char *e = getenv("KSP_LANES");
+        int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : (v > MAX_LANES ? MAX_LANES : v);
+    }();
+    static const int64_t env_chunk = [] {
+        const char *c = getenv("KSP_CHUNK");
+        return c ? (int64_t) atoll(c) : (int64_t) 0;
+    }();
+    int lanes = env_lanes;
     int64_t chunk = p->chunk_baselines;
     if (chunk <= 0) {
-        const char *c = getenv("KSP_CHUNK");
-        chunk = c ? atoll(c) : 0;
+        chunk = env_chunk;
         if (chunk <= 0) {
             // Whole waves: with 16 baselines per SM a chunk is exactly 16 waves of the
             // background kernel (4 blocks of 32 baselines x 256 channels per SM, 32768 channels)
@@ -90,7 +99,10 @@ Layout make_layout(const ksp_flagger_params *p)
                 int64_t k = (p->baselines + (int64_t) lanes * unit / 2) / ((int64_t) lanes * unit);
                 chunk = unit * (k < 1 ? 1 : k);
             } else {
-                chunk = ksp_divup(ksp_divup(p->baselines, lanes), 32) * 32;
+                // a shard smaller than one unit (e.g. 1620 baselines of a 12960-baseline dump on
+                // 8 GPUs): one or two launches per stage, not `lanes` sub-wave ones
+                const int n = p->baselines * 2 > unit ? 2 : 1;
+                chunk = ksp_divup(ksp_divup(p->baselines, n), 32) * 32;
             }
         }
     }
@@ -114,13 +126,30 @@ Layout make_layout(const ksp_flagger_params *p)
 extern "C" size_t ksp_flagger_scratch_bytes(const ksp_flagger_params *p)
 {
     if (!p || p->channels <= 0 || p->baselines <= 0) return 0;
+    if (ksp_dataflow_applies(p)) return ksp_dataflow_scratch_bytes(p);
     Layout l = make_layout(p);
     return (l.dev_bytes + l.bits_bytes + l.work_bytes) * (size_t) l.lanes;
+}
+
+extern "C" int ksp_flagger_is_dataflow(const ksp_flagger_params *p)
+{
+    return (p && p->channels > 0 && p->baselines > 0 && ksp_dataflow_applies(p)) ? 1 : 0;
+}
+
+extern "C" int ksp_flagger_stats(void *stream, const ksp_flagger_params *p, const void *scratch,
+                                 unsigned long long *out, int n)
+{
+    if (!p || !out || n < 0) return KSP_EINVAL;
+    for (int i = 0; i < n; i++) out[i] = 0;
+    if (p->channels <= 0 || p->baselines <= 0 || !ksp_dataflow_applies(p)) return 0;
+    if (!scratch) return KSP_EINVAL;
+    return ksp_dataflow_stats((cudaStream_t) stream, scratch, out, n);
 }
 
 extern "C" int64_t ksp_flagger_chunk_baselines(const ksp_flagger_params *p)
 {
     if (!p || p->channels <= 0 || p->baselines <= 0) return 0;
+    if (ksp_dataflow_applies(p)) return 32;                 // the dataflow kernel's strip
     return make_layout(p).chunk;
 }
 
@@ -135,6 +164,10 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
     if (p->n_windows < 1) return KSP_EINVAL;
     if (p->flag_mode != KSP_FLAGS_NONE && !input_flags) return KSP_EINVAL;
     if (p->flags_stride < p->baselines || p->vis_stride < p->baselines) return KSP_EINVAL;
+    if (p->chunk_baselines < 0 && !ksp_dataflow_legal(p)) return KSP_EINVAL;
+    if (ksp_dataflow_applies(p))
+        return ksp_dataflow_flagger((cudaStream_t) stream, p, vis, input_flags, noise, flags, scratch,
+                                    scratch_bytes);
     Layout l = make_layout(p);
     const size_t lane_bytes = l.dev_bytes + l.bits_bytes + l.work_bytes;
     if (scratch_bytes < lane_bytes * (size_t) l.lanes) return KSP_ESCRATCH;
@@ -154,7 +187,8 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
     }
 
     int64_t index = 0;
-    for (int64_t b0 = 0; b0 < p->baselines; b0 += l.chunk, index++) {
+    int status = 0;                        // first error; the lanes are joined before it is returned
+    for (int64_t b0 = 0; b0 < p->baselines && !status; b0 += l.chunk, index++) {
         const int lane = (int) (index % l.lanes);
         cudaStream_t s = pool ? pool->stream[lane] : user;
         float *dev_t = (float *) ((char *) scratch + lane_bytes * (size_t) lane);
@@ -170,27 +204,29 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
                                                 p->width, p->is_amplitude, p->flag_mode,
                                                 p->abs_mode);
         ksp_profile_end(KSP_STAGE_BACKGROUND, s);
-        if (rc) return rc;
+        if (rc) { status = rc; break; }
         ksp_profile_begin(KSP_STAGE_NOISE, s);
         rc = ksp_madnz_t(s, dev_t, noise + b0, p->channels, nb, l.dev_stride);
         ksp_profile_end(KSP_STAGE_NOISE, s);
-        if (rc) return rc;
+        if (rc) { status = rc; break; }
         ksp_profile_begin(KSP_STAGE_THRESHOLD, s);
         rc = ksp_threshold_sum_packed(s, dev_t, noise + b0, bits_t, p->channels, nb, l.dev_stride,
                                       l.words_stride, p->n_windows, p->n_sigma, p->scales, work);
         ksp_profile_end(KSP_STAGE_THRESHOLD, s);
-        if (rc) return rc;
+        if (rc) { status = rc; break; }
         ksp_profile_begin(KSP_STAGE_EXPAND, s);
         rc = ksp_expand_flags(s, bits_t, flags + b0, p->channels, nb, l.words_stride,
                               p->flags_stride, p->flag_value);
         ksp_profile_end(KSP_STAGE_EXPAND, s);
-        if (rc) return rc;
+        if (rc) { status = rc; break; }
     }
     if (pool) {
+        // always: later work on the caller's stream must not overtake kernels still running on a lane
         for (int i = 0; i < l.lanes; i++) {
-            KSP_CUDA(cudaEventRecord(pool->done[i], pool->stream[i]));
-            KSP_CUDA(cudaStreamWaitEvent(user, pool->done[i], 0));
+            cudaError_t e = cudaEventRecord(pool->done[i], pool->stream[i]);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(user, pool->done[i], 0);
+            if (e != cudaSuccess && !status) status = (int) e;
         }
     }
-    return 0;
+    return status;
 }

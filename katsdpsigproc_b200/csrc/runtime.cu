@@ -18,6 +18,7 @@ const char *ksp_error_string(int code)
     case KSP_ESCRATCH: return "scratch buffer too small";
     case KSP_ENOJIT: return "run-time compiler (NVRTC) not available";
     case KSP_EJIT: return "run-time compilation failed (see ksp_jit_log)";
+    case KSP_ETIMEOUT: return "the dataflow flagger abandoned a launch (a wait exceeded its limit)";
     default: break;
     }
     if (code > 0) return cudaGetErrorString((cudaError_t) code);

@@ -29,6 +29,7 @@ from __future__ import annotations
 
 import enum
 from abc import ABC, abstractmethod
+import ctypes
 from ctypes import byref, c_double, c_size_t
 from typing import Any, List, Mapping, Optional, Tuple, Union
 
@@ -479,9 +480,13 @@ class ThresholdSumDevice(AbstractThresholdDevice):
 class FusedFlaggerDevice(accel.Operation):
     """Median background + MAD noise + SumThreshold as one operation (``ksp_flagger``).
 
-    Works through the baselines in chunks whose intermediates (baseline-major
-    deviations, bit-packed flags) live in ``scratch`` and stay L2-resident, so HBM
-    sees the visibilities once and the flags once.
+    Width 13, up to 7 window sizes, channels a multiple of 32 (from 2048 channels): ONE
+    persistent "dataflow" kernel per dump whose work items (background tiles, noise rows,
+    threshold spans, flag expansion tiles) hand the baseline-major deviations on through a ring of
+    a few strips of 32 baselines in ``scratch``; the ring is small enough (48 MB at 32768
+    channels) to stay in the L2 cache, so device memory sees the visibilities once and the flags
+    once.  Anything else, or ``chunk_baselines > 0``: four launches per chunk of baselines with
+    the whole chunk's deviations in ``scratch`` (they do go through device memory).
 
     Slots: **vis**, **flags** (input flags; only with ``use_flags``), **noise**,
     **out_flags** (channels x baselines uint8) and **scratch** (uint8 bytes).
@@ -528,6 +533,7 @@ class FusedFlaggerDevice(accel.Operation):
         lib = _capi.load()
         self.scratch_bytes = int(lib.ksp_flagger_scratch_bytes(byref(params)))
         self.chunk_baselines = int(lib.ksp_flagger_chunk_baselines(byref(params)))
+        self.dataflow = bool(lib.ksp_flagger_is_dataflow(byref(params)))
         self._params = params
         self.slots["scratch"] = accel.IOSlot((max(self.scratch_bytes, 16),), np.uint8)
 
@@ -545,6 +551,14 @@ class FusedFlaggerDevice(accel.Operation):
                ptr(in_flags) if in_flags is not None else None, ptr(self.buffer("noise")),
                ptr(out), ptr(scratch), c_size_t(self.scratch_bytes))
 
+    def stats(self) -> Mapping[str, int]:
+        """Diagnostics of the last run (waits for the queue): per-kind SM cycles, wait cycles,
+        items, noise fallbacks of the dataflow kernel; raises if it abandoned the launch."""
+        out = (ctypes.c_ulonglong * len(_capi.DF_STAT_NAMES))()
+        launch(self.command_queue, "ksp_flagger_stats", byref(self._params),
+               ptr(self.buffer("scratch")), out, len(out))
+        return dict(zip(_capi.DF_STAT_NAMES, (int(v) for v in out)))
+
     def parameters(self) -> Mapping[str, Any]:
         return {
             "width": self.background_template.width,
@@ -554,6 +568,7 @@ class FusedFlaggerDevice(accel.Operation):
             "threshold_falloff": self.threshold_falloff,
             "flag_value": self.threshold_template.flag_value,
             "chunk_baselines": self.chunk_baselines,
+            "dataflow": self.dataflow,
             "channels": self.channels,
             "baselines": self.baselines,
         }
@@ -679,9 +694,14 @@ class FlaggerDevice(accel.OperationSequence):
                 operations.append(("transpose_flags", self.transpose_flags))
         super().__init__(command_queue, operations, compounds, allocator=allocator)
 
+    def stats(self) -> Mapping[str, int]:
+        """Diagnostics of the fused operation's last run (see FusedFlaggerDevice.stats)."""
+        return self.fused_op.stats() if self.fused_op is not None else {}
+
     def parameters(self) -> Mapping[str, Any]:
         return {
             "fused": self.fused_op is not None,
+            "dataflow": self.fused_op is not None and self.fused_op.dataflow,
             "channels": self.channels,
             "baselines": self.baselines,
         }

@@ -216,7 +216,16 @@ def flagger(vis: np.ndarray, input_flags: Optional[np.ndarray] = None, *, width:
     scratch = Dev((max(n_scratch, 16),), np.uint8)
     _capi.call("ksp_flagger", None, byref(p), dvis.p, fp, noise.p, flags.p, scratch.p,
                c_size_t(n_scratch))
+    stats = (ctypes.c_ulonglong * len(_capi.DF_STAT_NAMES))()
+    _capi.call("ksp_flagger_stats", None, byref(p), scratch.p, stats, len(stats))  # raises if abandoned
+    LAST_FLAGGER_STATS.clear()
+    LAST_FLAGGER_STATS.update(zip(_capi.DF_STAT_NAMES, (int(v) for v in stats)))
+    LAST_FLAGGER_STATS["dataflow"] = int(_capi.load().ksp_flagger_is_dataflow(byref(p)))
     return flags.get(), noise.get()
+
+
+# diagnostics of the most recent flagger() call (ksp_flagger_stats + whether the dataflow form ran)
+LAST_FLAGGER_STATS: dict = {}
 
 
 def selection_fallbacks(reset: bool = False) -> int:

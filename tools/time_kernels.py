@@ -106,9 +106,20 @@ def main():
         nbytes = _capi.load().ksp_flagger_scratch_bytes(byref(prm))
         used = _capi.load().ksp_flagger_chunk_baselines(byref(prm))
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        rec(f"flagger_fused_chunk{used}", timeit(lambda: _capi.call(
+        dataflow = bool(_capi.load().ksp_flagger_is_dataflow(byref(prm)))
+        flags.fill_(0x55)
+        name = "flagger_dataflow" if dataflow else f"flagger_fused_chunk{used}"
+        rec(name, timeit(lambda: _capi.call(
             "ksp_flagger", S, byref(prm), p(vis), None, p(noise), p(flags), p(scratch),
             c_size_t(nbytes)), args.reps, flush), 9)
+        st = (ctypes.c_ulonglong * len(_capi.DF_STAT_NAMES))()
+        _capi.call("ksp_flagger_stats", S, byref(prm), p(scratch), st, len(st))
+        res[name]["scratch_MB"] = round(nbytes / 1e6, 1)
+        res[name]["flags_sum"] = int(flags.sum(dtype=torch.int64))
+        res[name]["noise_sum"] = float(noise.double().sum())
+        if dataflow:
+            res[name]["stats"] = dict(zip(_capi.DF_STAT_NAMES, (int(v) for v in st)))
+        print(name, res[name], flush=True)
         del scratch
     print("flagged fraction (fused)", float(flags.float().mean()))
     if not args.only_fused:
@@ -124,7 +135,7 @@ def main():
         rec("maskedsum_c64", timeit(lambda: _capi.call(
             "ksp_maskedsum", S, p(vis), p(mask), p(dest), C, B, B, 0, 0), args.reps, flush), 8)
     os.makedirs("gpurun_out", exist_ok=True)
-    with open("gpurun_out/time_kernels.json", "w") as f:
+    with open(os.environ.get("TK_OUT", "gpurun_out/time_kernels.json"), "w") as f:
         json.dump({"channels": C, "baselines": B, "results": res}, f, indent=1)
 
 
