@@ -8,7 +8,7 @@
 //
 //   step t:  background tiles of strip t,
 //            noise rows of strip t - L1,
-//            threshold spans of strip t - L2,
+//            threshold rows of strip t - L2,
 //            a quarter of the expansion tiles of the group (4 strips) that finished L3 steps ago
 //
 // Every block (256 threads, 4 per SM) takes the next item with one atomic ticket, waits until
@@ -58,7 +58,7 @@ struct DfArgs {
     int T;                     // staged runs per threshold span (multiple of 32, <= 256)
     int n_chunks, chunk_valid, edge;
     int S, G;                  // strips, groups of 4 strips
-    int n_bg, n_thr, n_exp, n_expq, K, steps;
+    int n_bg, n_exp, n_expq, K, steps;
     uint32_t total;            // steps * K items
     int L1, L2, L3, R, RB;
     uint32_t *ctl;             // [0] ticket, [1] error
@@ -104,7 +104,7 @@ __device__ __forceinline__ int strip_rows(const DfArgs &a, int s)
 // Block-wide bookkeeping in shared memory: nothing of it occupies registers across the items.
 struct DfShared {
     long long cycles[6];       // per kind of item, [4] waiting, [5] start of the current item
-    uint64_t mbar;             // TMA completion barrier of the threshold spans
+    uint64_t mbar[2];          // TMA completion barriers of the two threshold span buffers
     uint32_t ticket, parity, items;
     int go;
     int strip, tile, row_off;  // the current background tile (see WhereInRing)
@@ -157,7 +157,7 @@ __device__ __noinline__ bool df_background(int s, int tile)
     if (threadIdx.x == 0) {
         int go = 1;
         if (s >= a.R)                      // the ring slot's previous strip has been thresholded
-            go = df_wait(&a.thr_done[s - a.R], (uint32_t) (strip_rows(a, s - a.R) * a.n_chunks),
+            go = df_wait(&a.thr_done[s - a.R], (uint32_t) strip_rows(a, s - a.R),
                          &a.ctl[1], sh->cycles[4]);
         sh->go = go;
         sh->strip = s;
@@ -206,26 +206,27 @@ __device__ __noinline__ uint32_t df_threshold_full(const TsTile &tl)
     return F;
 }
 
-// ---- threshold span y of row r of strip s
-__device__ __noinline__ bool df_threshold(const CUtensorMap *tmap, int s, int r, int y)
+// ---- threshold of row r of strip s: its spans one after the other, the next span's TMA load in
+//      flight while this one is worked on
+__device__ __noinline__ bool df_threshold(const CUtensorMap *tmap, int s, int r)
 {
     const DfArgs &a = s_args;
     DfShared *sh = &s_sh;
     uint8_t *sm = df_smem();
     const int tid = threadIdx.x;
     const int T = a.T;
-    // layout: span of (T + 2) runs, statistics, flag words, carries, thresholds
+    // layout: two spans of (T + 2) runs, statistics, flag words, carries, thresholds
     const int buf_floats = (((T + 2) * PITCH + 255) / 256) * 256;
-    float *rowbuf = reinterpret_cast<float *>(sm);
-    float4 *stat = reinterpret_cast<float4 *>(rowbuf + buf_floats);             // DF_THREADS + 2
-    uint32_t *Fsm = reinterpret_cast<uint32_t *>(stat + DF_THREADS + 2);         // DF_THREADS + 2
+    float *rowbuf0 = reinterpret_cast<float *>(sm);
+    float4 *stat = reinterpret_cast<float4 *>(rowbuf0 + 2 * buf_floats);         // T + 2 (<= DF_THREADS + 2)
+    uint32_t *Fsm = reinterpret_cast<uint32_t *>(stat + DF_THREADS + 2);         // T + 2
     uint32_t *car1 = Fsm + DF_THREADS + 2;                                       // DF_THREADS
     uint32_t *car2 = car1 + DF_THREADS;                                          // DF_THREADS
     float *thr = reinterpret_cast<float *>(car2 + DF_THREADS);                   // 8
-    const int base = y * a.chunk_valid - a.edge;                                 // row channel of slot 0
     const int64_t b = (int64_t) s * 32 + r;
+    const int ring_row = 32 * (s % a.R) + r;
     // this shared memory was last written with ordinary stores (previous item): order them before
-    // the TMA write of the span
+    // the TMA writes of the spans
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
@@ -236,8 +237,11 @@ __device__ __noinline__ bool df_threshold(const CUtensorMap *tmap, int s, int r,
             // the deviations were written with ordinary stores by other blocks: order them before
             // this block's reads through the async proxy
             asm volatile("fence.proxy.async;" ::: "memory");
-            mbar_expect_tx(&sh->mbar, (uint32_t) T * RUN * 4u);
-            tma_load_3d(rowbuf, tmap, 0, base >> 5, 32 * (s % a.R) + r, &sh->mbar);
+            for (int y = 0; y < 2 && y < a.n_chunks; y++) {
+                mbar_expect_tx(&sh->mbar[y], (uint32_t) T * RUN * 4u);
+                tma_load_3d(rowbuf0 + y * buf_floats, tmap, 0, (y * a.chunk_valid - a.edge) >> 5, ring_row,
+                            &sh->mbar[y]);
+            }
         }
         sh->go = go;
     }
@@ -245,27 +249,43 @@ __device__ __noinline__ bool df_threshold(const CUtensorMap *tmap, int s, int r,
         Fsm[T + tid - 32] = 0u;
         stat[T + tid - 32] = make_float4(-__int_as_float(0x7f800000), 0.0f, 0.0f, 0.0f);
     }
-    if (tid >= 64 && tid < 64 + 2 * PITCH) rowbuf[T * PITCH + tid - 64] = 0.0f;
+    if (tid >= 64 && tid < 64 + 2 * PITCH) {               // two runs of zeros past each span
+        rowbuf0[T * PITCH + tid - 64] = 0.0f;
+        rowbuf0[buf_floats + T * PITCH + tid - 64] = 0.0f;
+    }
+    if (tid >= 128 && tid < 128 + a.n_windows)
+        thr[tid - 128] = 0.0f;                                 // (set below, once the noise may be read)
     __syncthreads();
     if (!sh->go) return false;
     if (tid < a.n_windows)
         thr[tid] = __double2float_rn((a.n_sigma * (double) __ldcg(a.noise + b)) * a.scales[tid]);
-    mbar_wait(&sh->mbar, sh->parity);
-    __syncthreads();
     const int C = (int) a.bg.channels;
-    const int64_t pos0 = (int64_t) base + (int64_t) tid * RUN;
-    uint32_t F = 0;
-    TsTile tl;
-    tl.rowbuf = rowbuf; tl.stat = stat; tl.Fsm = Fsm; tl.car1 = car1; tl.car2 = car2; tl.thr = thr;
-    tl.T = T; tl.span = T * RUN; tl.C = C; tl.n_windows = a.n_windows; tl.pos0 = pos0;
-    if (ts_process_tile<true>(tl, F)) F = df_threshold_full(tl);   // block-uniform
-    const int64_t out_lo = (int64_t) y * a.chunk_valid;
-    const int64_t out_hi = min((int64_t) C, out_lo + (int64_t) a.chunk_valid);
-    if (tid < T && pos0 >= out_lo && pos0 < out_hi)
-        a.bits[((int64_t) 32 * (s % a.RB) + r) * a.words_stride + (pos0 >> 5)] =
-            F & bit_range(-pos0, (int64_t) C - pos0);
+    uint32_t *bits_row = a.bits + ((int64_t) 32 * (s % a.RB) + r) * a.words_stride;
+    for (int y = 0; y < a.n_chunks; y++) {
+        float *rowbuf = rowbuf0 + (y & 1) * buf_floats;
+        mbar_wait(&sh->mbar[y & 1], (sh->parity >> (y & 1)) & 1u);
+        __syncthreads();                   // thr[] visible; the previous span's statistics are free
+        const int base = y * a.chunk_valid - a.edge;               // row channel of slot 0
+        const int64_t pos0 = (int64_t) base + (int64_t) tid * RUN;
+        uint32_t F = 0;
+        TsTile tl;
+        tl.rowbuf = rowbuf; tl.stat = stat; tl.Fsm = Fsm; tl.car1 = car1; tl.car2 = car2; tl.thr = thr;
+        tl.T = T; tl.span = T * RUN; tl.C = C; tl.n_windows = a.n_windows; tl.pos0 = pos0;
+        if (ts_process_tile<true>(tl, F)) F = df_threshold_full(tl);   // block-uniform
+        const int64_t out_lo = (int64_t) y * a.chunk_valid;
+        const int64_t out_hi = min((int64_t) C, out_lo + (int64_t) a.chunk_valid);
+        if (tid < T && pos0 >= out_lo && pos0 < out_hi)
+            bits_row[pos0 >> 5] = F & bit_range(-pos0, (int64_t) C - pos0);
+        __syncthreads();                   // everybody is done with this buffer
+        if (tid == 0) {
+            sh->parity ^= 1u << (y & 1);
+            if (y + 2 < a.n_chunks) {
+                mbar_expect_tx(&sh->mbar[y & 1], (uint32_t) T * RUN * 4u);
+                tma_load_3d(rowbuf, tmap, 0, ((y + 2) * a.chunk_valid - a.edge) >> 5, ring_row, &sh->mbar[y & 1]);
+            }
+        }
+    }
     df_complete(&a.thr_done[s], sh, 2);
-    if (tid == 0) sh->parity ^= 1u;
     return true;
 }
 
@@ -278,7 +298,7 @@ __device__ __noinline__ bool df_expand(int g, int tile)
     if (threadIdx.x == 0) {
         int go = 1;
         for (int s = 4 * g; s < 4 * g + 4 && s < a.S && go; s++)
-            go = df_wait(&a.thr_done[s], (uint32_t) (strip_rows(a, s) * a.n_chunks), &a.ctl[1], sh->cycles[4]);
+            go = df_wait(&a.thr_done[s], (uint32_t) strip_rows(a, s), &a.ctl[1], sh->cycles[4]);
         sh->go = go;
     }
     __syncthreads();
@@ -303,7 +323,8 @@ dataflow_kernel(const __grid_constant__ DfArgs a_param, const __grid_constant__ 
         for (int i = tid; i < (int) (sizeof(DfArgs) / 4); i += DF_THREADS) dst[i] = src[i];
     }
     if (tid == 0) {
-        mbar_init(&s_sh.mbar, 1);
+        mbar_init(&s_sh.mbar[0], 1);
+        mbar_init(&s_sh.mbar[1], 1);
         for (int i = 0; i < 6; i++) s_sh.cycles[i] = 0;
         s_sh.parity = 0;
         s_sh.items = 0;
@@ -328,12 +349,11 @@ dataflow_kernel(const __grid_constant__ DfArgs a_param, const __grid_constant__ 
         } else if ((slot -= a.n_bg) < 32) {
             const int s = step - a.L1;
             if (s >= 0 && s < a.S && slot < strip_rows(a, s)) ok = df_noise(s, slot);
-        } else if ((slot -= 32) < a.n_thr) {
+        } else if ((slot -= 32) < 32) {
             const int s = step - a.L2;
-            const int r = slot / a.n_chunks, y = slot - r * a.n_chunks;
-            if (s >= 0 && s < a.S && r < strip_rows(a, s)) ok = df_threshold(&tmap, s, r, y);
+            if (s >= 0 && s < a.S && slot < strip_rows(a, s)) ok = df_threshold(&tmap, s, slot);
         } else {
-            slot -= a.n_thr;
+            slot -= 32;
             const int e = step - a.L3;
             const int g = e >> 2, tile = (e & 3) * a.n_expq + slot;
             if (e >= 0 && g < a.G && tile < a.n_exp) ok = df_expand(g, tile);
@@ -351,14 +371,16 @@ dataflow_kernel(const __grid_constant__ DfArgs a_param, const __grid_constant__ 
     }
 }
 
+constexpr int DF_SPAN_RUNS = 160;        // runs of 32 channels per staged threshold span: two buffers fit
 constexpr size_t df_thr_smem(int T)
 {
-    return (size_t) ((((T + 2) * PITCH + 255) / 256) * 256) * 4 + (size_t) (DF_THREADS + 2) * 16 +
+    return 2 * (size_t) ((((T + 2) * PITCH + 255) / 256) * 256) * 4 + (size_t) (DF_THREADS + 2) * 16 +
            (size_t) (DF_THREADS + 2) * 4 + (size_t) DF_THREADS * 8 + 64;
 }
 constexpr size_t cmax(size_t x, size_t y) { return x > y ? x : y; }
 constexpr size_t DF_SMEM = 1024 + cmax(cmax((size_t) TileGeom<BG_TC>::SMEM_BYTES, (size_t) MS_SMEM_WORDS * 4),
-                                       cmax(df_thr_smem(DF_THREADS), (size_t) EXPAND_SMEM_WORDS * 4));
+                                       cmax(df_thr_smem(DF_SPAN_RUNS), (size_t) EXPAND_SMEM_WORDS * 4));
+static_assert(DF_SMEM <= 56 * 1024, "four blocks per SM");
 
 int env_int(const char *name, int def, int lo, int hi)
 {
@@ -401,7 +423,7 @@ DfLayout df_layout(const ksp_flagger_params *p)
     l.S = (int) ksp_divup(p->baselines, 32);
     l.G = (l.S + 3) / 4;
     const int64_t runs = p->channels / RUN;
-    if (runs <= DF_THREADS) {
+    if (runs <= DF_SPAN_RUNS) {
         l.T = (int) (ksp_divup(runs, 32) * 32);
         l.edge = 0;
         l.chunk_valid = l.T * RUN;
@@ -409,7 +431,7 @@ DfLayout df_layout(const ksp_flagger_params *p)
     } else {
         const int reach = (1 << p->n_windows) - p->n_windows - 1;      // influence radius of a sample
         l.edge = (int) (ksp_divup(reach, RUN) * RUN);
-        const int max_valid = DF_THREADS * RUN - 2 * l.edge;
+        const int max_valid = DF_SPAN_RUNS * RUN - 2 * l.edge;
         int n = (int) ksp_divup(p->channels, max_valid);
         int valid = (int) (ksp_divup(ksp_divup(p->channels, n), RUN) * RUN);
         l.T = (int) (ksp_divup((valid + 2 * l.edge) / RUN, 32) * 32);
@@ -509,10 +531,9 @@ int ksp_dataflow_flagger(cudaStream_t s, const ksp_flagger_params *p, const void
     a.T = l.T; a.n_chunks = l.n_chunks; a.chunk_valid = l.chunk_valid; a.edge = l.edge;
     a.S = l.S; a.G = l.G;
     a.n_bg = (int) ksp_divup(p->channels, BG_TC);
-    a.n_thr = 32 * l.n_chunks;
     a.n_exp = (int) ksp_divup(p->channels / 32, 8);
     a.n_expq = (a.n_exp + 3) / 4;
-    a.K = a.n_bg + 32 + a.n_thr + a.n_expq;
+    a.K = a.n_bg + 32 + 32 + a.n_expq;
     a.L1 = c.L1; a.L2 = c.L2; a.L3 = c.L3;
     a.R = c.R < l.S ? c.R : l.S;
     a.RB = c.RB < 4 * l.G ? c.RB : 4 * l.G;

@@ -50,7 +50,8 @@ def check(vis, input_flags=None, *, n_windows=7, n_sigma=11.0, abs_mode, amplitu
 
 @pytest.mark.parametrize("channels,baselines", [
     (32, 1), (64, 5), (256, 33), (512, 128), (2048, 96), (4096, 130), (8192, 31),
-    (8224, 40),        # just over one span: two threshold spans per row
+    (5152, 40),        # just over one span: two threshold spans per row
+    (8224, 40),
     (10240, 64), (32768, 70),
     (2048, 1000),      # 32 strips: both rings wrap several times
     (1024, 3000),
@@ -59,10 +60,9 @@ def test_shapes(abs_mode, channels, baselines):
     rs = np.random.RandomState(channels + baselines)
     st = check(make_vis(rs, channels, baselines), abs_mode=abs_mode, n_sigma=5.0)
     strips = -(-baselines // 32)
-    spans = 1 if channels <= 8192 else -(-channels // (256 * 32 - 256))
-    expected = strips * -(-channels // 256) + baselines + baselines * spans \
-        + -(-strips // 4) * -(-channels // 256)
-    assert st["items"] >= expected * 0.99            # span count is the library's choice
+    tiles = -(-channels // 256)
+    # background tiles, noise rows, threshold rows, expansion tiles
+    assert st["items"] == strips * tiles + 2 * baselines + -(-strips // 4) * tiles
 
 
 @pytest.mark.parametrize("n_windows", [1, 2, 4, 6, 7])
