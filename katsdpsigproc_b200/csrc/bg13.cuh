@@ -306,6 +306,7 @@ struct BlockTile {               // grid (strips, channel tiles)
     template <int TC> __device__ __forceinline__ int c0() const { return (int) blockIdx.y * TC; }
     __device__ __forceinline__ int64_t b0() const { return (int64_t) blockIdx.x * 32; }
     __device__ __forceinline__ int64_t row_off() const { return 0; }
+    static constexpr bool KEEP_IN_L2 = false;
 };
 
 template <int IN_MODE, int FLAG_MODE, bool TRANSPOSED, int TC, typename Where, int PF = BG_PF>
@@ -371,8 +372,13 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
             if (TRANSPOSED) {
                 float *o = a.out + (b + row_off) * a.out_stride + c;
                 if (c + 7 < C && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
-                    reinterpret_cast<float4 *>(o)[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
-                    reinterpret_cast<float4 *>(o)[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+                    if (Where::KEEP_IN_L2) {
+                        stg_keep_f4(o, make_float4(o8[0], o8[1], o8[2], o8[3]));
+                        stg_keep_f4(o + 4, make_float4(o8[4], o8[5], o8[6], o8[7]));
+                    } else {
+                        reinterpret_cast<float4 *>(o)[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+                        reinterpret_cast<float4 *>(o)[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+                    }
                 } else {
 #pragma unroll
                     for (int k = 0; k < 8; k++)

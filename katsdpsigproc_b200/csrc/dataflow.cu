@@ -106,6 +106,8 @@ struct DfShared {
     long long cycles[6];       // per kind of item, [4] waiting, [5] start of the current item
     uint64_t mbar[2];          // TMA completion barriers of the two threshold span buffers
     uint32_t ticket, parity, items;
+    uint32_t *counter;         // what the item that just ran has to bump (null: nothing)
+    int kind;                  // its kind, for the time accounting
     int go;
     int strip, tile, row_off;  // the current background tile (see WhereInRing)
 };
@@ -131,17 +133,17 @@ struct WhereInRing {
     template <int TC> __device__ __forceinline__ int c0() const { return sh->tile * TC; }
     __device__ __forceinline__ int64_t b0() const { return (int64_t) sh->strip * 32; }
     __device__ __forceinline__ int64_t row_off() const { return (int64_t) sh->row_off; }
+    static constexpr bool KEEP_IN_L2 = true;     // the ring is read twice and overwritten while in L2
 };
 
-// Item done: publish its writes, bump the strip's (group's) counter, account the time.
+// Item done: say which counter to bump.  The scheduling loop does it after its next barrier (all
+// of the item's writes are then complete), on another warp than the one that fetches the next
+// ticket, so that the fence and the ticket's round trip overlap.
 __device__ __forceinline__ void df_complete(uint32_t *counter, DfShared *sh, int kind)
 {
-    __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(counter, 1u);
-        sh->cycles[kind] += clock64() - sh->cycles[5];
-        sh->items++;
+        sh->counter = counter;
+        sh->kind = kind;
     }
 }
 
@@ -169,12 +171,9 @@ __device__ __noinline__ bool df_background(int s, int tile)
     WhereInRing at;
     at.sh = sh;
     bg13_tile<IN_MODE, FLAG_MODE, true, BG_TC, WhereInRing, DF_BG_PF>(a.bg, at, reinterpret_cast<float *>(sm));
-    __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(&a.bg_done[sh->strip], 1u);
-        sh->cycles[0] += clock64() - sh->cycles[5];
-        sh->items++;
+        sh->counter = &a.bg_done[sh->strip];
+        sh->kind = 0;
     }
     return true;
 }
@@ -328,17 +327,33 @@ dataflow_kernel(const __grid_constant__ DfArgs a_param, const __grid_constant__ 
         for (int i = 0; i < 6; i++) s_sh.cycles[i] = 0;
         s_sh.parity = 0;
         s_sh.items = 0;
+        s_sh.counter = nullptr;
+        s_sh.kind = -1;
+        s_sh.cycles[5] = clock64();
     }
     for (;;) {
-        __syncthreads();                  // the previous item's shared memory is free
+        __syncthreads();                  // the previous item's writes are done, its shared memory is free
         const DfArgs &a = s_args;
+        if (threadIdx.x == 32 && s_sh.counter) {       // publish the previous item
+            __threadfence();
+            atomicAdd(s_sh.counter, 1u);
+        }
         if (threadIdx.x == 0) {
             uint32_t t = atomicAdd(&a.ctl[0], 1u);
+            const long long now = clock64();
+            if (s_sh.kind >= 0) {
+                s_sh.cycles[s_sh.kind] += now - s_sh.cycles[5];
+                s_sh.items++;
+            }
+            s_sh.cycles[5] = now;
             if (*reinterpret_cast<volatile uint32_t *>(&a.ctl[1]) != 0u) t = 0xffffffffu;
             s_sh.ticket = t;
-            s_sh.cycles[5] = clock64();
         }
         __syncthreads();
+        if (threadIdx.x == 0) {           // (thread 32 has read them)
+            s_sh.counter = nullptr;
+            s_sh.kind = -1;
+        }
         const uint32_t ticket = s_sh.ticket;
         if (ticket >= a.total) break;
         const int step = (int) (ticket / (uint32_t) a.K);

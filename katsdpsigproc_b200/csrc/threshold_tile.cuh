@@ -400,10 +400,11 @@ __device__ __forceinline__ void expand_flags_tile(const uint32_t *__restrict__ b
             const uint32_t t2 = __byte_perm(b01, b23, 0x5410);  // channel 4g + 2
             const uint32_t t3 = __byte_perm(b01, b23, 0x7632);  // channel 4g + 3
             uint8_t *o = out + (int64_t) (4 * g) * fstride;
-            *reinterpret_cast<uint32_t *>(o) = t0;
-            *reinterpret_cast<uint32_t *>(o + fstride) = t1;
-            *reinterpret_cast<uint32_t *>(o + 2 * fstride) = t2;
-            *reinterpret_cast<uint32_t *>(o + 3 * fstride) = t3;
+            // write-once output: first to leave the L2
+            stg_stream_u32(reinterpret_cast<uint32_t *>(o), t0);
+            stg_stream_u32(reinterpret_cast<uint32_t *>(o + fstride), t1);
+            stg_stream_u32(reinterpret_cast<uint32_t *>(o + 2 * fstride), t2);
+            stg_stream_u32(reinterpret_cast<uint32_t *>(o + 3 * fstride), t3);
         }
         return;
     }
