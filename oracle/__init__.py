@@ -21,3 +21,23 @@ Two tiers ("Oracle"):
     bit; it must match ``host_numpy`` as the rules say (selections exact,
     noise within 1 ulp, flags exact outside a counted 1e-6 band).
 """
+
+
+import importlib
+import os
+import sys
+from typing import Any, Optional
+
+
+def reference_host() -> Optional[Any]:
+    """The reference's own ``katsdpsigproc.rfi.host`` module from ``oracle/_ref`` (placed there
+    by ``oracle/make_ref.py`` in the build container), or ``None`` if it is not there."""
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+    if not os.path.isfile(os.path.join(root, "katsdpsigproc", "rfi", "host.py")):
+        return None
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    try:
+        return importlib.import_module("katsdpsigproc.rfi.host")
+    except Exception:
+        return None
