@@ -12,10 +12,13 @@ so there is no data-path collective and scaling is weak.
 
 The JSON line carries: ``value`` (device-resident input, CUDA-event timed, max over
 ranks), ``e2e`` (through the public FlaggerDevice API from pinned host buffers,
-H2D + kernels + D2H inside the timed region), ``roofline`` (dominant kernel, timed
-live with CUDA events on the flagger's stream), ``cpu_baseline`` (the numpy/pandas
-port of the reference's FlaggerHost on this box's host cores; rank 0, N=1 only),
-``clocks`` and ``gpu_launches``.
+H2D + kernels + D2H inside the timed region), ``parity`` (flags and noise of a
+deterministic subset of this very dump against the host classes, in the same run),
+``roofline`` (the flagger's kernel, timed live with CUDA events on its stream; the
+four stages of the chunked form beside it), ``cfg5`` (BASELINE.json configs[4]: ONE
+32768 x 12960 dump sharded over the ranks by baseline ranges, blocks of 16 dumps),
+``cpu_baseline`` (the reference's FlaggerHost on this box's host cores; rank 0, N=1
+only), ``clocks`` and ``gpu_launches``.
 """
 
 from __future__ import annotations
@@ -53,13 +56,35 @@ def _cpu_worker(args):
     warnings.filterwarnings("ignore")
     from oracle import host_numpy
 
+    run = host_flagger()[0]
     vis, _ = host_numpy.synthetic_vis(channels, baselines, seed=seed)
     while time.time() < start_at:       # line the workers up so that they contend as in a real run
         time.sleep(0.001)
     t0 = time.perf_counter()
-    host_numpy.flagger(vis, None, width=WIDTH, n_sigma=N_SIGMA, n_windows=N_WINDOWS,
-                       threshold_falloff=FALLOFF)
+    run(vis)
     return time.perf_counter() - t0, channels * baselines
+
+
+def host_flagger():
+    """(callable vis -> flags, kind, description): the UNMODIFIED reference FlaggerHost from
+    oracle/_ref when it is there (placed by oracle/make_ref.py where the reference checkout
+    exists), else its numpy/pandas restatement oracle/host_numpy.py."""
+    import oracle
+    from oracle import host_numpy
+
+    ref = oracle.reference_host()
+    if ref is not None:
+        fn = ref.FlaggerHost(ref.BackgroundMedianFilterHost(WIDTH), ref.NoiseEstMADHost(),
+                             ref.ThresholdSumHost(N_SIGMA, n_windows=N_WINDOWS,
+                                                  threshold_falloff=FALLOFF))
+        return fn, "reference", ("katsdpsigproc.rfi.host.FlaggerHost, unmodified (oracle/_ref), one "
+                                 "process per host core")
+
+    def port(vis):
+        return host_numpy.flagger(vis, None, width=WIDTH, n_sigma=N_SIGMA, n_windows=N_WINDOWS,
+                                  threshold_falloff=FALLOFF)
+    return port, "port", ("oracle/host_numpy.py (numpy/pandas restatement of the reference's "
+                          "FlaggerHost), one process per host core")
 
 
 def host_cores() -> int:
@@ -97,6 +122,7 @@ def reference_arm(args) -> None:
     cores = host_cores()
     steps = max(1, args.steps)
     value, ms, sample = cpu_flagger_rate(args.channels, steps, args.warmup, cores)
+    _, kind, what = host_flagger()
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": UNIT,
@@ -104,8 +130,8 @@ def reference_arm(args) -> None:
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": sample, "what": what},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -194,13 +220,34 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def source_sha16() -> str:
+    """Fingerprint of the CUDA sources the library is built from."""
+    import glob
+    import hashlib
+
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "katsdpsigproc_b200", "csrc")
+    names = sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh"))
+                   + glob.glob(os.path.join(csrc, "*.h")) + [os.path.join(csrc, "Makefile")])
+    for name in names:
+        with open(name, "rb") as f:
+            h.update(os.path.basename(name).encode() + b"\0" + f.read())
+    return h.hexdigest()[:16]
+
+
 def ncu_traffic(kernel: str):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+    """(DRAM bytes per launch of `kernel`, note) from the committed ncu capture
+    profiles/roofline_traffic.json - only if that capture was taken from THESE sources."""
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(kernel)
+            rec = json.load(f)
     except Exception:
-        return None
+        return None, "no capture committed"
+    sha = source_sha16()
+    if rec.get("source_sha16") != sha:
+        return None, (f"capture {rec.get('tag')} is of sources {rec.get('source_sha16')}, "
+                      f"this build is {sha}: not reported")
+    return rec.get("kernels", {}).get(kernel), f"ncu --set full capture {rec.get('tag')} of these sources"
 
 
 def b200_arm(args) -> None:
@@ -213,9 +260,9 @@ def b200_arm(args) -> None:
         # before CUDA is initialised in this process: the workers are forked
         cores = host_cores()
         value, ms, sample = cpu_flagger_rate(args.channels, 2, 1, cores)
-        cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
-               "what": "oracle/host_numpy.py (numpy/pandas restatement of the reference's "
-                       "FlaggerHost), one process per host core"}
+        _, kind, what = host_flagger()
+        cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample,
+               "what": what}
 
     import numpy as np
     import torch
@@ -325,35 +372,56 @@ def b200_arm(args) -> None:
         barrier()
     flagged = float(np.count_nonzero(flags_host[:, :B])) / n_vis
 
-    # ---- dominant kernel, timed live with CUDA events around every stage launch
+    peak, peak_source = measured_peak()
+    stats = dict(flagger.stats()) if template.fused else {}
+    dataflow = bool(flagger.parameters().get("dataflow"))
+
+    # ---- parity of THIS dump, in this run: a deterministic subset of baselines at full channel
+    # count ({0..63} U every 65th U last 64) against the host classes
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_block(flagger, queue, C, B)
+
+    # ---- the chunked four-kernel form of the same flagger: the four stages timed one after
+    # the other (one lane, CUDA events around every launch) and as it runs (4 lanes)
+    chunked = None
+    if template.fused and not args.no_stages:
+        chunked = chunked_form(template, queue, flagger, C, B, min(args.steps, 5), timed, peak)
+
     roofline = None
     if template.fused:
-        _capi.profile_enable(True)
-        for _ in range(args.steps):
-            flagger()
-        queue.finish()
-        stages = _capi.profile_read()
-        _capi.profile_enable(False)
-        per_unit = {"background": 12.0, "noise": 4.0, "threshold": 4.125, "expand_flags": 1.125}
-        top = max(stages, key=lambda k: stages[k][0])
-        top_ms, top_launches = stages[top]
-        peak, peak_source = measured_peak()
-        achieved = per_unit[top] * n_vis * args.steps / (top_ms * 1e-3) / 1e9
-        kernel_names = {"background": "bg13_kernel", "noise": "madnz_stream_kernel",
-                        "threshold": "threshold_sum_kernel", "expand_flags": "expand_flags_kernel"}
+        kernel = "dataflow_kernel" if dataflow else (
+            max(chunked["stage_ms_per_step"], key=chunked["stage_ms_per_step"].get) if chunked else "flagger")
+        achieved = 9.0 * n_vis / (ms_step * 1e-3) / 1e9
+        traffic, traffic_note = ncu_traffic(kernel)
         roofline = {
-            "bound": "hbm", "kernel": kernel_names[top],
+            "bound": "hbm", "kernel": kernel,
             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "peak_source": peak_source,
-            "traffic": ncu_traffic(kernel_names[top]),
-            "algorithmic_bytes_per_vis": per_unit[top],
-            "launch_ms": top_ms / max(top_launches, 1),
-            "launches_per_step": top_launches / args.steps,
-            "stage_ms_per_step": {k: v[0] / args.steps for k, v in stages.items()},
-            "pipeline_bytes_per_vis": 9.0,
-            "pipeline_achieved": 9.0 * n_vis / (ms_step * 1e-3) / 1e9,
-            "pipeline_frac": 9.0 * n_vis / (ms_step * 1e-3) / 1e9 / peak,
+            "traffic": traffic, "traffic_source": traffic_note,
+            "algorithmic_bytes_per_vis": 9.0,
+            "launch_ms": ms_step / max(launches / args.steps, 1),
+            "launches_per_step": launches / args.steps,
+            "pipeline_bytes_per_vis": 9.0, "pipeline_achieved": achieved,
+            "pipeline_frac": achieved / peak,
         }
+        if dataflow and stats:
+            busy = sum(stats[k] for k in ("cycles_background", "cycles_noise", "cycles_threshold",
+                                          "cycles_expand")) or 1
+            roofline["work_item_share"] = {
+                "background": stats["cycles_background"] / busy, "noise": stats["cycles_noise"] / busy,
+                "threshold": stats["cycles_threshold"] / busy, "expand_flags": stats["cycles_expand"] / busy,
+                "of_which_waiting_for_other_items": stats["cycles_wait"] / busy,
+                "what": "block-cycles per kind of work item of the last launch (ksp_flagger_stats)"}
+            roofline["noise_rows_redone_by_radix_select"] = stats["fallbacks"]
+        if chunked:
+            roofline["chunked_form"] = chunked
+
+    # ---- BASELINE.json configs[4]: ONE 32768 x 12960 dump sharded by baseline ranges
+    cfg5 = None
+    if not args.no_cfg5:
+        del stream
+        cfg5 = cfg5_block(template, queue, context, rank, world, barrier, reduce_max, args)
 
     if rank == 0:
         total_vis = n_vis * world
@@ -365,7 +433,7 @@ def b200_arm(args) -> None:
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": dict(workload_config(args, world), fused=bool(template.fused),
-                           injected_fraction=injected, flagged_fraction=flagged),
+                           dataflow=dataflow, injected_fraction=injected, flagged_fraction=flagged),
             "e2e": {"value": total_vis / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e,
@@ -375,12 +443,224 @@ def b200_arm(args) -> None:
                                     if bound_cpus else "none")},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
+            "parity": parity,
             "roofline": roofline,
+            "cfg5": cfg5,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_subset(baselines: int):
+    import numpy as np
+
+    idx = set(range(min(64, baselines))) | set(range(0, baselines, 65)) | \
+        set(range(max(0, baselines - 64), baselines))
+    return np.array(sorted(idx))
+
+
+def parity_block(flagger, queue, C: int, B: int) -> dict:
+    """Flags and noise of the benchmarked dump as the device left them, for a subset of
+    baselines, against (a) the float32 device contract (oracle/contract.c; must be identical),
+    (b) the host classes in float64 - the unmodified reference FlaggerHost when oracle/_ref
+    holds it, and its numpy port, which also counts the window decisions that lie within 1e-6
+    (relative) of their threshold, the only places where a flag may legitimately differ."""
+    import warnings
+
+    import numpy as np
+
+    from oracle import contract
+    from oracle import host_numpy as hn
+
+    t0 = time.perf_counter()
+    flagger()                                           # the device buffers hold this dump's results
+    pick = parity_subset(B)
+    vis = np.ascontiguousarray(np.array(flagger.buffer("vis").get(queue))[:, pick])
+    flags = np.ascontiguousarray(np.array(flagger.buffer("flags").get(queue))[:, pick])
+    noise = np.array(flagger.buffer("noise").get(queue))[pick]
+    abs_mode = contract.detect_abs_mode()
+    c_flags, _, c_noise = contract.flagger(vis, None, width=WIDTH, n_sigma=N_SIGMA,
+                                           n_windows=N_WINDOWS, threshold_falloff=FALLOFF,
+                                           abs_mode=abs_mode)
+    near, stages = {}, {}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        h_flags = hn.flagger(vis, None, width=WIDTH, n_sigma=N_SIGMA, n_windows=N_WINDOWS,
+                             threshold_falloff=FALLOFF, stages=stages, near=near)
+        run, kind, _ = host_flagger()
+        r_flags = run(vis) if kind == "reference" else None
+    h_noise = stages["noise"].astype(np.float32)
+    ulp = np.abs(noise.view(np.int32).astype(np.int64) - h_noise.view(np.int32).astype(np.int64))
+    out = {
+        "shape": [C, B], "baselines_checked": int(pick.size),
+        "flag_mismatches": int(np.count_nonzero(flags != h_flags)),
+        "near_threshold_1e-6": int(near.get("band", 0)),
+        "noise_max_ulp": int(ulp.max()),
+        "contract_flag_mismatches": int(np.count_nonzero(flags != c_flags)),
+        "contract_noise_mismatches": int(np.count_nonzero(noise.view(np.uint32) != c_noise.view(np.uint32))),
+        "flags_checked": int(flags.size), "flags_set": int(np.count_nonzero(flags)),
+        "host": "oracle/host_numpy.py (FlaggerHost restated, float64)",
+        "seconds": None,
+    }
+    if r_flags is not None:
+        out["reference_flag_mismatches"] = int(np.count_nonzero(flags != r_flags))
+        out["reference"] = "katsdpsigproc.rfi.host.FlaggerHost, unmodified (oracle/_ref)"
+    out["seconds"] = round(time.perf_counter() - t0, 2)
+    return out
+
+
+def chunked_form(template, queue, flagger, C: int, B: int, steps: int, timed, peak: float) -> dict:
+    """The same flagger as four launches per chunk of baselines (ksp_flagger with
+    chunk_baselines > 0), sharing the main flagger's vis / noise / flags buffers."""
+    from ctypes import byref
+
+    from katsdpsigproc_b200 import _capi
+    from katsdpsigproc_b200.rfi import device as rfi_device
+
+    probe = rfi_device.FusedFlaggerDevice(template.background, template.threshold, queue, C, B,
+                                          N_SIGMA, FALLOFF, chunk_baselines=16 * 148)
+    probe.bind(vis=flagger.buffer("vis"), noise=flagger.buffer("noise"),
+               out_flags=flagger.buffer("flags"))
+    probe.ensure_all_bound()
+    for _ in range(2):
+        probe()
+    queue.finish()
+    ms_lanes = timed(probe, steps)
+    _capi.profile_enable(True)
+    for _ in range(steps):
+        probe()
+    queue.finish()
+    stages = _capi.profile_read()
+    _capi.profile_enable(False)
+    per_unit = {"background": 12.0, "noise": 4.0, "threshold": 4.125, "expand_flags": 1.125}
+    names = {"background": "bg13_kernel", "noise": "madnz_stream_kernel",
+             "threshold": "threshold_sum_kernel (two passes)", "expand_flags": "expand_flags_kernel"}
+    n_vis = C * B
+    out = {
+        "what": "four launches per chunk of 2368 baselines; deviations go through device memory",
+        "ms_per_step_4_lanes": ms_lanes,
+        "ms_per_step_1_lane_sum_of_stages": sum(v[0] for v in stages.values()) / steps,
+        "stage_ms_per_step": {k: v[0] / steps for k, v in stages.items()},
+        "stage_launches_per_step": {k: v[1] / steps for k, v in stages.items()},
+        "stage_kernel": names,
+        "stage_algorithmic_bytes_per_vis": per_unit,
+        "stage_frac_of_peak": {k: per_unit[k] * n_vis * steps / (v[0] * 1e-3) / 1e9 / peak
+                               for k, v in stages.items() if v[0] > 0},
+    }
+    del probe
+    return out
+
+
+CFG5_BASELINES = 12960
+CFG5_DUMPS = 16
+
+
+def cfg5_block(template, queue, context, rank: int, world: int, barrier, reduce_max, args) -> dict:
+    """BASELINE.json configs[4]: one 32768 x 12960 dump (80 antennas, 4 polarisations) split
+    into contiguous baseline ranges, one per rank (sharding.baseline_ranges), flagged in blocks
+    of 16 dumps.  Device-resident time per dump (max over ranks), end to end through
+    StreamingFlagger, and - with several ranks - the whole dump on rank 0 alone, timed in the
+    same run, for the strong-scaling ratio."""
+    import numpy as np
+    import torch
+
+    from katsdpsigproc_b200 import _capi, sharding, streaming
+
+    C = args.channels
+    start, stop = sharding.baseline_ranges(CFG5_BASELINES, world)[rank]
+    nb = stop - start
+    targs = {"n_sigma": N_SIGMA, "threshold_falloff": FALLOFF}
+
+    def make(nbl, seed):
+        fl = template.instantiate(queue, C, nbl, threshold_args=targs)
+        fl.ensure_all_bound()
+        vis = fl.buffer("vis")
+        stride = vis.padded_shape[1]
+        torch.manual_seed(seed)
+        gen = torch.zeros(C, stride, 2, device="cuda", dtype=torch.float32)
+        gen[:, :nbl].normal_()
+        hit = torch.rand(C, nbl, device="cuda") < (1.0 / 64.0)
+        gen[:, :nbl, 0] += hit * (torch.rand(C, nbl, device="cuda") * 20.0 + 50.0)
+        del hit
+        torch.cuda.synchronize()
+        _capi.call("ksp_memcpy_async", vis.ptr, gen.data_ptr(), gen.numel() * 4, _capi.D2D, queue.stream)
+        queue.finish()
+        del gen
+        torch.cuda.empty_cache()
+        return fl
+
+    def time_block(fl, dumps):
+        for _ in range(3):
+            fl()
+        queue.finish()
+        barrier()
+        a = queue.enqueue_marker()
+        for _ in range(dumps):
+            fl()
+        b = queue.enqueue_marker()
+        queue.finish()
+        barrier()
+        return 1e3 * b.time_since(a) / dumps
+
+    fl = make(nb, 100 + rank)
+    ms_shard = reduce_max(time_block(fl, CFG5_DUMPS))
+    out = {
+        "workload": (f"ONE {C} x {CFG5_BASELINES} complex64 dump sharded by baseline ranges over "
+                     f"{world} rank(s), blocks of {CFG5_DUMPS} dumps (BASELINE.json configs[4])"),
+        "baselines_this_rank": nb, "shards": sharding.shard_sizes(CFG5_BASELINES, world),
+        "dumps_per_block": CFG5_DUMPS,
+        "ms_per_dump": ms_shard,
+        "value": C * CFG5_BASELINES / (ms_shard * 1e-3), "unit": UNIT,
+        "dataflow": bool(fl.parameters().get("dataflow")),
+        "launches_per_dump": None,
+    }
+    n0 = _capi.kernel_launch_count()
+    fl()
+    queue.finish()
+    out["launches_per_dump"] = _capi.kernel_launch_count() - n0
+    # end to end: every dump of the block uploaded from pinned host memory, flags downloaded
+    stream = streaming.StreamingFlagger(template, C, nb, depth=2, threshold_args=targs)
+    first = fl.buffer("vis").get(queue, stream.host_vis(0))
+    for k in range(1, stream.depth):
+        np.copyto(stream.host_vis(k), first)
+    del fl
+    for _ in range(stream.depth):
+        stream.submit(None)
+    stream.drain()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(CFG5_DUMPS):
+        stream.submit(None)
+    stream.drain()
+    torch.cuda.synchronize()
+    ms_e2e = reduce_max(1e3 * (time.perf_counter() - t0) / CFG5_DUMPS)
+    barrier()
+    out["e2e"] = {"ms_per_dump": ms_e2e, "value": C * CFG5_BASELINES / (ms_e2e * 1e-3), "unit": UNIT,
+                  "h2d_bytes_per_dump_this_rank": int(np.prod(first.shape)) * 8}
+    del stream, first
+    if world > 1:
+        # the whole dump on ONE GPU, same run: rank 0 works, the others wait at the barrier
+        ms_full = 0.0
+        if rank == 0:
+            full = make(CFG5_BASELINES, 100)
+            for _ in range(3):
+                full()
+            queue.finish()
+            a = queue.enqueue_marker()
+            for _ in range(CFG5_DUMPS):
+                full()
+            b = queue.enqueue_marker()
+            queue.finish()
+            ms_full = 1e3 * b.time_since(a) / CFG5_DUMPS
+            del full
+        barrier()
+        ms_full = reduce_max(ms_full)
+        out["ms_per_dump_whole_dump_on_one_gpu"] = ms_full
+        out["strong_scaling_speedup"] = ms_full / ms_shard
+        out["strong_scaling_efficiency"] = ms_full / ms_shard / world
+    return out
 
 
 def main() -> None:
@@ -395,8 +675,16 @@ def main() -> None:
     ap.add_argument("--unfused", action="store_true",
                     help="run the reference's 5-operation sequence instead of the fused flagger")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity block")
+    ap.add_argument("--no-stages", action="store_true",
+                    help="skip the chunked form's per-stage timings")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the configs[4] block")
+    ap.add_argument("--quick", action="store_true",
+                    help="only the two timed legs: no CPU baseline, parity, stages or cfg5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else max(args.warmup, 0)
+    if args.quick:
+        args.no_cpu_baseline = args.no_parity = args.no_stages = args.no_cfg5 = True
     if args.impl == "reference":
         reference_arm(args)
     else:

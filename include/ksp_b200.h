@@ -173,8 +173,8 @@ int ksp_maskedsum(void *stream, const void *src, const float *mask, void *dest, 
  * Fused flagger: the standard median + MAD + SumThreshold combination of
  * rfi/device.py:1111-1166 (5 launches, 31 B/vis of memory traffic in the reference).
  *
- * Dataflow form (width 13, up to 7 window sizes, channels a multiple of 32; the default from
- * 2048 channels): ONE persistent kernel per dump.  Background tiles, noise rows, threshold
+ * Dataflow form (width 13, up to 7 window sizes, channels a multiple of 32; chosen with
+ * chunk_baselines < 0 or KSP_DATAFLOW=1): ONE persistent kernel per dump.  Background tiles, noise rows, threshold
  * spans and bit -> byte expansion tiles are work items of one schedule; the deviations pass
  * from item to item through a ring of a few strips of 32 baselines that stays in the L2 cache,
  * so device memory sees the visibilities once and the flags once.
@@ -196,9 +196,9 @@ typedef struct ksp_flagger_params {
     int flag_value;
     double n_sigma;
     double scales[KSP_MAX_WINDOWS];
-    int64_t chunk_baselines;     /* 0 = library's choice (dataflow form where it applies, else one chunk
-                                  * per lane: KSP_LANES, default 4; KSP_CHUNK); > 0 = chunked form with
-                                  * this chunk; < 0 = dataflow form or KSP_EINVAL */
+    int64_t chunk_baselines;     /* 0 = library's choice (the chunked form, one chunk per lane: KSP_LANES,
+                                  * default 4; KSP_CHUNK; KSP_DATAFLOW=1: the dataflow form where legal);
+                                  * > 0 = chunked form with this chunk; < 0 = dataflow form or KSP_EINVAL */
 } ksp_flagger_params;
 
 size_t ksp_flagger_scratch_bytes(const ksp_flagger_params *p);

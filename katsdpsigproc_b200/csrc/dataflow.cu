@@ -221,7 +221,7 @@ __device__ __noinline__ bool df_threshold(const CUtensorMap *tmap, int s, int r)
     uint32_t *Fsm = reinterpret_cast<uint32_t *>(stat + DF_THREADS + 2);         // T + 2
     uint32_t *car1 = Fsm + DF_THREADS + 2;                                       // DF_THREADS
     uint32_t *car2 = car1 + DF_THREADS;                                          // DF_THREADS
-    float *thr = reinterpret_cast<float *>(car2 + DF_THREADS);                   // 8
+    float *thr = reinterpret_cast<float *>(car2 + DF_THREADS);                   // TS_THR_WORDS
     const int64_t b = (int64_t) s * 32 + r;
     const int ring_row = 32 * (s % a.R) + r;
     // this shared memory was last written with ordinary stores (previous item): order them before
@@ -252,12 +252,10 @@ __device__ __noinline__ bool df_threshold(const CUtensorMap *tmap, int s, int r)
         rowbuf0[T * PITCH + tid - 64] = 0.0f;
         rowbuf0[buf_floats + T * PITCH + tid - 64] = 0.0f;
     }
-    if (tid >= 128 && tid < 128 + a.n_windows)
-        thr[tid - 128] = 0.0f;                                 // (set below, once the noise may be read)
     __syncthreads();
     if (!sh->go) return false;
-    if (tid < a.n_windows)
-        thr[tid] = __double2float_rn((a.n_sigma * (double) __ldcg(a.noise + b)) * a.scales[tid]);
+    if (tid < 32)
+        ts_thresholds(thr, tid, a.n_windows, a.n_sigma, __ldcg(a.noise + b), a.scales, (int) a.bg.channels);
     const int C = (int) a.bg.channels;
     uint32_t *bits_row = a.bits + ((int64_t) 32 * (s % a.RB) + r) * a.words_stride;
     for (int y = 0; y < a.n_chunks; y++) {
@@ -390,7 +388,7 @@ constexpr int DF_SPAN_RUNS = 160;        // runs of 32 channels per staged thres
 constexpr size_t df_thr_smem(int T)
 {
     return 2 * (size_t) ((((T + 2) * PITCH + 255) / 256) * 256) * 4 + (size_t) (DF_THREADS + 2) * 16 +
-           (size_t) (DF_THREADS + 2) * 4 + (size_t) DF_THREADS * 8 + 64;
+           (size_t) (DF_THREADS + 2) * 4 + (size_t) DF_THREADS * 8 + TS_THR_WORDS * 4;
 }
 constexpr size_t cmax(size_t x, size_t y) { return x > y ? x : y; }
 constexpr size_t DF_SMEM = 1024 + cmax(cmax((size_t) TileGeom<BG_TC>::SMEM_BYTES, (size_t) MS_SMEM_WORDS * 4),
@@ -503,7 +501,12 @@ bool ksp_dataflow_applies(const ksp_flagger_params *p)
     if (p->chunk_baselines > 0 || !ksp_dataflow_legal(p)) return false;
     if (p->chunk_baselines < 0) return true;
     if (c.mode >= 0) return c.mode == 1;
-    return p->channels >= 2048;          // short rows: the items are too small to pay for their tickets
+    // Measured on B200 (profiles/r02*): 1.9 - 2.4 ms per 32768 x 8320 dump against 1.18 ms for the
+    // chunked form - four 256-thread item streams per SM leave every item's serial chain (ticket,
+    // dependency, load, compute, publish) exposed, where the stand-alone kernels run 4 to 9 smaller
+    // blocks per SM.  So the library's own choice is the chunked form; this one is there for callers
+    // that would rather spare the device-memory traffic (9 instead of 20 bytes per visibility).
+    return false;
 }
 
 size_t ksp_dataflow_scratch_bytes(const ksp_flagger_params *p)

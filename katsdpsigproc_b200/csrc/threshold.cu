@@ -87,8 +87,8 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
     uint32_t *Fsm = reinterpret_cast<uint32_t *>(stat + T + 2);             // T + 2
     uint32_t *car1 = Fsm + T + 2;                              // T
     uint32_t *car2 = car1 + T;                                 // T
-    float *thr = reinterpret_cast<float *>(car2 + T);          // TS_MAX_WINDOWS (+1)
-    uint64_t *mbar = reinterpret_cast<uint64_t *>(thr + 8);    // TMA completion barriers, one per buffer
+    float *thr = reinterpret_cast<float *>(car2 + T);          // TS_THR_WORDS
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(thr + TS_THR_WORDS);   // TMA completion barriers, one per buffer
 
     const int C = (int) a.channels;
     const int64_t total = a.baselines * (int64_t) a.n_chunks;  // tiles = (row, span) pairs
@@ -128,7 +128,7 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
     const int step_y = (int) ((int64_t) gridDim.x - step_rows * a.n_chunks);
     // the noise of a tile's row is fetched one tile ahead, like its samples
     float noise_now = 0.0f;
-    if (tid < a.n_windows && (int64_t) blockIdx.x < n_iter) noise_now = a.noise[row];
+    if (tid < 32 && (int64_t) blockIdx.x < n_iter) noise_now = a.noise[row];
     if (a.use_tma && a.two_buffers && tid == 0 && (int64_t) blockIdx.x < n_iter) issue_tile(row, span_y, 0);
 
     // ---- persistent loop over tiles; with two buffers the next tile's load is in flight while
@@ -151,8 +151,8 @@ threshold_sum_kernel(const TsArgs a, const __grid_constant__ CUtensorMap tmap)
 
     // (everybody has left the previous tile's last barrier: thr, Fsm, stat and the other buffer
     // are free)
-    if (tid < a.n_windows) {
-        thr[tid] = __double2float_rn((a.n_sigma * (double) noise_now) * a.scales[tid]);
+    if (tid < 32) {
+        ts_thresholds(thr, tid, a.n_windows, a.n_sigma, noise_now, a.scales, C);
         if (has_next) noise_now = a.noise[next_row];
     }
 
@@ -432,7 +432,7 @@ size_t ts_smem_bytes(int threads, int buffers)
     // span buffer(s), 7 words of state per run, thresholds and mbarriers, + 1 KB so that the
     // spans can be aligned for the swizzle
     const size_t buf_floats = ((((size_t) threads + 2) * PITCH + 255) / 256) * 256;   // whole KB
-    return sizeof(float) * ((size_t) buffers * buf_floats + 7 * ((size_t) threads + 2) + 16) + 1024 + 16;
+    return sizeof(float) * ((size_t) buffers * buf_floats + 7 * ((size_t) threads + 2) + 32) + 1024 + 16;
 }
 
 // Blocks of the persistent grid: as many as fit on the device at once.

@@ -139,13 +139,41 @@ __device__ __noinline__ uint32_t window_candidates(const float *rowbuf, int r, u
     return cand;
 }
 
+// Per-window thresholds of one row (noise `noise`) and the thread-invariant parts of the vote,
+// computed by ONE WARP (all 32 lanes call it; lane = its lane number) into thr[0 .. TS_THR_WORDS):
+//   thr[w], w < n_windows   thr_w = f32((n_sigma * f64(noise)) * scales[w])
+//   thr[8]                  strictest limit of the sizes 2..8 that exist (+inf if none)
+//   thr[9] (bits)           bit 0: some existing size has a negative threshold (everything is
+//                           hot); bits 4..6: sizes 16 / 32 / 64 exist with a threshold >= 0
+// A size "exists" if it is below n_windows, not larger than the band and its threshold is not NaN.
+constexpr int TS_THR_WORDS = 16;
+__device__ __forceinline__ void ts_thresholds(float *thr, int lane, int n_windows, double n_sigma,
+                                              float noise, const double *scales, int C)
+{
+    const float inf = __int_as_float(0x7f800000);
+    float tw = 0.0f;
+    if (lane < n_windows) tw = __double2float_rn((n_sigma * (double) noise) * scales[lane]);
+    const bool exists = lane >= 1 && lane < n_windows && (1 << lane) <= C && tw == tw;
+    const bool neg = exists && !(tw >= 0.0f);
+    const unsigned some_neg = __ballot_sync(0xffffffffu, neg);
+    const unsigned plain = __ballot_sync(0xffffffffu, exists && !neg);
+    float lim = (exists && !neg && lane <= 3) ? __fmul_rd(tw, 0.99999905f) : inf;
+    lim = fminf(lim, __shfl_xor_sync(0xffffffffu, lim, 1));
+    lim = fminf(lim, __shfl_xor_sync(0xffffffffu, lim, 2));
+    if (lane < n_windows) thr[lane] = tw;
+    if (lane == 0) {
+        thr[8] = lim;
+        thr[9] = __uint_as_float((some_neg ? 1u : 0u) | (plain & 0x70u));
+    }
+}
+
 // One staged span, processed by the T threads that staged it (thread <-> run of 32 channels).
 struct TsTile {
     const float *rowbuf;   // the span, swizzled, T + 2 runs (two runs of zeros at the end)
     float4 *stat;          // T + 2 run statistics (entries T, T + 1 preset: -inf, 0, 0, 0)
     uint32_t *Fsm;         // T + 2 flag words (entries T, T + 1 preset to 0)
     uint32_t *car1, *car2; // T words each
-    const float *thr;      // per-window thresholds
+    const float *thr;      // per-window thresholds and vote constants (ts_thresholds)
     int T, span, C, n_windows;   // T: staged runs; threads tid >= T only take part in the barriers
     int64_t pos0;          // row channel of this thread's element 0
 };
@@ -185,12 +213,18 @@ __device__ __forceinline__ bool ts_process_tile(const TsTile &t, uint32_t &F)
         if (first) {
             // window size 1: flag and zero in one go (samples outside the band are zeros and
             // stay zeros whether or not their bit survives the mask)
+            // (three instructions per sample: compare, predicated OR of the flag bit, predicated zero)
             const float t0 = thr[0];
 #pragma unroll
             for (int j = 0; j < RUN; j++) {
-                const bool f = x[j] > t0;
-                F |= f ? (1u << j) : 0u;
-                x[j] = f ? 0.0f : x[j];
+                asm("{\n\t"
+                    ".reg .pred p;\n\t"
+                    "setp.gt.f32 p, %1, %2;\n\t"
+                    "@p or.b32 %0, %0, %3;\n\t"
+                    "@p mov.f32 %1, 0f00000000;\n\t"
+                    "}"
+                    : "+r"(F), "+f"(x[j])
+                    : "f"(t0), "r"(1u << j));
             }
             F &= in_range;
         } else {
@@ -261,25 +295,14 @@ __device__ __forceinline__ bool ts_process_tile(const TsTile &t, uint32_t &F)
     // limits (one comparison against the largest sample within reach), sizes 16..64 keep the
     // positive-sum bound, and band edges are ignored (a false "maybe" only costs the loop).
     {
-        float lim_small = __int_as_float(0x7f800000);          // strictest limit of the sizes <= 8
-        bool any = false;
+        const float lim_small = thr[8];                        // strictest limit of the sizes <= 8
+        const uint32_t kinds = __float_as_uint(thr[9]);
+        bool any = (kinds & 1u) != 0u;                         // a negative threshold: everything is hot
         const int nf1 = __popc(F) + __popc(F1), nf2 = nf1 + __popc(F2);
         const float bound1 = ppos + st1.y, bound2 = bound1 + st2.y;
-        for (int w = 1; w < t.n_windows; w++) {
-            const int win = 1 << w;
-            if (win > C) break;
-            const float tw = thr[w];
-            if (tw != tw) continue;
-            if (!(tw >= 0.0f)) {
-                any = true;                                    // negative threshold: everything is hot
-            } else if (win <= 8) {
-                lim_small = fminf(lim_small, __fmul_rd(tw, 0.99999905f));
-            } else {
-                const bool two = win > RUN;
-                const float t_min = tw * (float) max(win - (two ? nf2 : nf1), 0);
-                any |= !((two ? bound2 : bound1) <= __fmul_rd(t_min, 0.99999f));
-            }
-        }
+        if (kinds & 0x10u) any |= !(bound1 <= __fmul_rd(thr[4] * (float) max(16 - nf1, 0), 0.99999f));
+        if (kinds & 0x20u) any |= !(bound1 <= __fmul_rd(thr[5] * (float) max(32 - nf1, 0), 0.99999f));
+        if (kinds & 0x40u) any |= !(bound2 <= __fmul_rd(thr[6] * (float) max(64 - nf2, 0), 0.99999f));
         const float reach_max = fmaxf(fmaxf(fmaxf(m8[0], m8[1]), fmaxf(m8[2], m8[3])), st1.x);
         any |= !(reach_max <= lim_small);
         if (!__syncthreads_or(any && active)) return false;

@@ -480,13 +480,15 @@ class ThresholdSumDevice(AbstractThresholdDevice):
 class FusedFlaggerDevice(accel.Operation):
     """Median background + MAD noise + SumThreshold as one operation (``ksp_flagger``).
 
-    Width 13, up to 7 window sizes, channels a multiple of 32 (from 2048 channels): ONE
-    persistent "dataflow" kernel per dump whose work items (background tiles, noise rows,
-    threshold spans, flag expansion tiles) hand the baseline-major deviations on through a ring of
-    a few strips of 32 baselines in ``scratch``; the ring is small enough (48 MB at 32768
-    channels) to stay in the L2 cache, so device memory sees the visibilities once and the flags
-    once.  Anything else, or ``chunk_baselines > 0``: four launches per chunk of baselines with
-    the whole chunk's deviations in ``scratch`` (they do go through device memory).
+    Default ("chunked" form): four launches per chunk of baselines (background written
+    baseline-major, noise, thresholds with bit-packed flags, expansion to channel-major bytes),
+    up to four chunks in flight; a chunk's deviations live in ``scratch`` and DO go through
+    device memory (written once, read twice: about 20 bytes of traffic per visibility).
+    ``chunk_baselines < 0`` ("dataflow" form; width 13, up to 7 window sizes, channels a multiple
+    of 32): ONE persistent kernel per dump whose work items (background tiles, noise rows,
+    threshold rows, flag expansion tiles) hand the deviations on through a ring of a few strips of
+    32 baselines that stays in the L2 cache, so device memory sees the visibilities once and the
+    flags once - less traffic, but measured slower on B200 than the chunked form.
 
     Slots: **vis**, **flags** (input flags; only with ``use_flags``), **noise**,
     **out_flags** (channels x baselines uint8) and **scratch** (uint8 bytes).

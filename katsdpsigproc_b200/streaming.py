@@ -99,8 +99,15 @@ class StreamingFlagger:
 
     def host_vis(self, index: Optional[int] = None) -> accel.HostArray:
         """The pinned staging array the NEXT (or ``index``-th) submission copies from; a
-        producer can write straight into it and call :meth:`submit` with ``None``."""
-        return self._slots[self._next if index is None else index].host_vis
+        producer can write straight into it and call :meth:`submit` with ``None``.
+
+        If that buffer set is still in flight, this first waits until its host -> device copy
+        has completed: the array may be overwritten as soon as it is returned.
+        """
+        slot = self._slots[self._next if index is None else index]
+        if slot.uploaded is not None:
+            slot.uploaded.wait()          # the asynchronous upload still reads the staging array
+        return slot.host_vis
 
     def submit(self, vis: Optional[np.ndarray], input_flags: Optional[np.ndarray] = None
                ) -> Optional[np.ndarray]:

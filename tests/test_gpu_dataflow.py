@@ -133,14 +133,15 @@ def test_repeated_launches_same_scratch(context, command_queue, abs_mode):
         rfi.BackgroundMedianFilterDeviceTemplate(context, 13, abs_mode=abs_mode),
         rfi.NoiseEstMADTDeviceTemplate(context, 1 << 20),
         rfi.ThresholdSumDeviceTemplate(context, n_windows=7))
-    fn = template.instantiate(command_queue, channels, baselines, threshold_args={"n_sigma": 11.0})
+    fn = rfi.FusedFlaggerDevice(template.background, template.threshold, command_queue, channels,
+                                baselines, 11.0, chunk_baselines=DATAFLOW)
     fn.ensure_all_bound()
     assert fn.parameters()["dataflow"]
     for _ in range(3):
         vis = make_vis(rs, channels, baselines)
         fn.buffer("vis").set(command_queue, vis)
         fn()
-        flags = np.array(fn.buffer("flags").get(command_queue))
+        flags = np.array(fn.buffer("out_flags").get(command_queue))
         noise = np.array(fn.buffer("noise").get(command_queue))
         st = fn.stats()
         assert st["error"] == 0 and st["items"] > 0

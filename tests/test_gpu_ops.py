@@ -360,6 +360,38 @@ def test_streaming_flagger(context, abs_mode, depth, use_flags):
         stream.submit(dumps[0], None if use_flags else np.zeros(channels, np.uint8))
 
 
+@pytest.mark.parametrize("depth", [1, 2])
+def test_streaming_flagger_zero_copy_staging(context, abs_mode, depth):
+    """The zero-copy pattern: the producer writes each dump straight into host_vis() and calls
+    submit(None).  host_vis() must not hand the staging array out while the upload of the dump
+    it still holds is in flight (large dumps, so that an upload takes a while)."""
+    from katsdpsigproc_b200 import streaming
+
+    channels, baselines = 4096, 1024
+    template = rfi.FlaggerDeviceTemplate(
+        rfi.BackgroundMedianFilterDeviceTemplate(context, 13, abs_mode=abs_mode),
+        rfi.NoiseEstMADTDeviceTemplate(context, 10240),
+        rfi.ThresholdSumDeviceTemplate(context, n_windows=7))
+    stream = streaming.StreamingFlagger(template, channels, baselines, depth=depth,
+                                        threshold_args={"n_sigma": 11.0})
+    rs = np.random.RandomState(6)
+    base = complex_normal(rs, (channels, baselines))
+    spike_sets, results = [], []
+    for i in range(6):
+        spikes = rs.random_sample(base.shape) < 1 / 256
+        spike_sets.append(spikes)
+        staging = stream.host_vis()
+        staging[...] = 0                              # a different dump every time
+        np.copyto(staging, base + (spikes * 80.0).astype(np.complex64))
+        out = stream.submit(None)
+        if out is not None:
+            results.append(out.copy())
+    results.extend(out.copy() for out in stream.drain())
+    assert len(results) == len(spike_sets)
+    for spikes, got in zip(spike_sets, results):
+        np.testing.assert_array_equal(spikes, got != 0)
+
+
 @pytest.mark.parametrize("depth", [1, 3])
 def test_async_streaming_flagger(context, abs_mode, depth):
     """The asyncio pipeline (Resource / JobQueue / async_wait_for_events): every task resolves to
