@@ -247,31 +247,33 @@ __device__ __forceinline__ bool tile_phase1_pipelined(const BgArgs &a, int64_t b
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int64_t b = min(b0 + lane, a.baselines - 1);
-    const int64_t row_bytes = a.vis_stride * 8;
+    const uint32_t row_bytes = (uint32_t) a.vis_stride * 8u;         // (the caller checks that it fits)
     const int n_it = (NEEDED - warp + NWARPS - 1) / NWARPS;          // groups warp, warp + 8, ...
     const char *p = reinterpret_cast<const char *>(a.vis) +
                     ((int64_t) (c0 - HALO_L + 4 * warp) * a.vis_stride + b) * 8;
-    const int64_t group_bytes = 4 * NWARPS * row_bytes;
     float *dst = amp_sm + lane * G::P + 4 * warp;
     float2 buf[PF + 1][4];
-    auto load = [&](float2 (&r)[4], const char *q) {
+    // row `row` of this thread's column: one multiply-add on the FMA pipe per address
+    // (IMAD.WIDE with an immediate row number) instead of a chain of 64-bit additions on the
+    // ALU pipe, which the selection network of phase 2 keeps busy
+    auto load = [&](float2 (&r)[4], int row) {
 #pragma unroll
         for (int k = 0; k < 4; k++) {
+            uint64_t q;
+            asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(q) : "r"(row_bytes), "r"((uint32_t) (row + k)),
+                "l"(reinterpret_cast<uint64_t>(p)));
             r[k] = ldg_stream_f2(reinterpret_cast<const float2 *>(q));
-            q += row_bytes;
         }
     };
 #pragma unroll
     for (int d = 0; d < PF; d++) {
-        if (d < n_it) load(buf[d], p);
-        p += group_bytes;
+        if (d < n_it) load(buf[d], 4 * NWARPS * d);
     }
     bool any_bad = false;
 #pragma unroll
     for (int it = 0; it < MAX_IT; it++) {
         if (it < n_it) {
-            if (it + PF < n_it) load(buf[(it + PF) % (PF + 1)], p);
-            p += group_bytes;
+            if (it + PF < n_it) load(buf[(it + PF) % (PF + 1)], 4 * NWARPS * (it + PF));
             const float2 (&r)[4] = buf[it % (PF + 1)];
             float v[4];
             unsigned redo = 0;
@@ -322,7 +324,8 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
         const int c0 = at.template c0<TC>();
         const bool interior = (c0 - HALO_L >= 0) && (c0 + TC + HALO_R <= C);   // block-uniform
         bool any_bad;
-        if (interior && IN_MODE == IN_NUMPY && FLAG_MODE == KSP_FLAGS_NONE && PF > 0)
+        if (interior && IN_MODE == IN_NUMPY && FLAG_MODE == KSP_FLAGS_NONE && PF > 0 &&
+            a.vis_stride < ((int64_t) 1 << 28))
             any_bad = tile_phase1_pipelined<IN_MODE, TC, PF>(a, b0, c0, amp_sm);
         else if (interior)
             any_bad = tile_phase1<IN_MODE, FLAG_MODE, true, TC>(a, b0, c0, amp_sm);
@@ -340,6 +343,9 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
     // 8 outputs: the 6 samples common to all 8 windows are sorted once (median13x8).
     if (!tile_bad) {
         constexpr int RUNS8 = TC / 8;
+        // whole tile inside the array and 16-byte aligned rows: no test per store (block-uniform)
+        const bool whole = TRANSPOSED && (b0 + TILE_B <= a.baselines) && (c0 + TC <= C) &&
+                           ((a.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
         for (int t = threadIdx.x; t < TILE_B * RUNS8; t += BG_THREADS) {
             int bl, j;
             if (TRANSPOSED) {
@@ -368,10 +374,10 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
             for (int k = 0; k < 8; k++) o8[k] = e[6 + k] - m[k];
             const int c = c0 + 8 * j;
             const int64_t b = b0 + bl;
-            if (b >= a.baselines || c >= C) continue;
+            if (!whole && (b >= a.baselines || c >= C)) continue;
             if (TRANSPOSED) {
                 float *o = a.out + (b + row_off) * a.out_stride + c;
-                if (c + 7 < C && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+                if (whole || (c + 7 < C && ((reinterpret_cast<uintptr_t>(o) & 15) == 0))) {
                     if (Where::KEEP_IN_L2) {
                         stg_keep_f4(o, make_float4(o8[0], o8[1], o8[2], o8[3]));
                         stg_keep_f4(o + 4, make_float4(o8[4], o8[5], o8[6], o8[7]));
