@@ -86,6 +86,54 @@ transpose_bytes_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ sr
     }
 }
 
+// Byte transpose, whole 128 x 128-byte tiles of 16-byte aligned arrays: 128-bit loads (a warp
+// reads 4 rows of 128 contiguous bytes), the tile kept as 32-bit words with an XOR swizzle
+// (word w of row r at w ^ 4 (r / 16): no padding, no bank conflicts either way), every thread
+// transposes a block of 16 rows x 4 columns in registers (4 x 4 byte transposes with PRMT) and
+// writes it as 4 rows of 16 bytes - 8 consecutive lanes fill 128 contiguous bytes of a row.
+__global__ void __launch_bounds__(256)
+transpose_bytes128_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src,
+                          int64_t dst_stride, int64_t src_stride)
+{
+    __shared__ __align__(16) uint32_t tile[128 * 32];
+    const int64_t c0 = (int64_t) blockIdx.x * 128;
+    const int64_t r0 = (int64_t) blockIdx.y * 128;
+    const int t = threadIdx.x;
+    uint4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int q = t + 256 * k, r = q >> 3, ch = q & 7;
+        v[k] = __ldcs(reinterpret_cast<const uint4 *>(src + (r0 + r) * src_stride + c0 + 16 * ch));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int q = t + 256 * k, r = q >> 3, ch = q & 7;
+        *reinterpret_cast<uint4 *>(&tile[r * 32 + ((4 * ch) ^ (4 * ((r >> 4) & 7)))]) = v[k];
+    }
+    __syncthreads();
+    const int lane = t & 31, warp = t >> 5;
+    const int rg = lane & 7, cw = 4 * warp + (lane >> 3);     // 16 rows 16 rg .., columns 4 cw .. 4 cw + 3
+    uint32_t w[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) w[i] = tile[(16 * rg + i) * 32 + (cw ^ (4 * rg))];
+    uint32_t o[4][4];                                         // o[k][g]: column byte k of rows 4 g .. 4 g + 3
+#pragma unroll
+    for (int g = 0; g < 4; g++) {
+        const uint32_t a01 = __byte_perm(w[4 * g], w[4 * g + 1], 0x5140);
+        const uint32_t b01 = __byte_perm(w[4 * g], w[4 * g + 1], 0x7362);
+        const uint32_t a23 = __byte_perm(w[4 * g + 2], w[4 * g + 3], 0x5140);
+        const uint32_t b23 = __byte_perm(w[4 * g + 2], w[4 * g + 3], 0x7362);
+        o[0][g] = __byte_perm(a01, a23, 0x5410);
+        o[1][g] = __byte_perm(a01, a23, 0x7632);
+        o[2][g] = __byte_perm(b01, b23, 0x5410);
+        o[3][g] = __byte_perm(b01, b23, 0x7632);
+    }
+    uint8_t *out = dst + (c0 + 4 * cw) * dst_stride + r0 + 16 * rg;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        __stcs(reinterpret_cast<uint4 *>(out + k * dst_stride), make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]));
+}
+
 template <typename T>
 int launch_tile(cudaStream_t s, void *dst, const void *src, int64_t rows, int64_t cols,
                 int64_t dst_stride, int64_t src_stride)
@@ -107,17 +155,42 @@ extern "C" int ksp_transpose(void *stream, void *dst, const void *src, int64_t r
     if (rows == 0 || cols == 0) return 0;
     if (!dst || !src) return KSP_EINVAL;
     cudaStream_t s = (cudaStream_t) stream;
+    if (elem_size != 1 && elem_size != 2 && elem_size != 4 && elem_size != 8 && elem_size != 16)
+        return KSP_EINVAL;
     if (((uintptr_t) dst | (uintptr_t) src) % (uintptr_t) elem_size) return KSP_EALIGN;
     switch (elem_size) {
     case 1: {
-        dim3 grid((unsigned) ksp_divup(cols, 64), (unsigned) ksp_divup(rows, 64));
-        if (grid.y > 65535) return KSP_ETOOLARGE;
+        const bool a16 = ((uintptr_t) dst % 16 == 0) && ((uintptr_t) src % 16 == 0) &&
+                         (dst_stride % 16 == 0) && (src_stride % 16 == 0);
+        // whole 128 x 128 tiles with the 128-bit kernel, the ragged right / bottom strips (and
+        // arrays that are not 16-byte aligned) with the 64 x 64 one
+        const int64_t r_main = a16 ? rows / 128 * 128 : 0, c_main = a16 ? cols / 128 * 128 : 0;
+        if (r_main > 0 && c_main > 0) {
+            dim3 grid((unsigned) (c_main / 128), (unsigned) (r_main / 128));
+            if (grid.y > 65535) return KSP_ETOOLARGE;
+            transpose_bytes128_kernel<<<grid, 256, 0, s>>>((uint8_t *) dst, (const uint8_t *) src,
+                                                           dst_stride, src_stride);
+            KSP_CHECK_LAUNCH();
+        }
         int vec_ok = ((uintptr_t) dst % 4 == 0) && ((uintptr_t) src % 4 == 0) &&
                      (dst_stride % 4 == 0) && (src_stride % 4 == 0);
-        transpose_bytes_kernel<<<grid, 256, 0, s>>>((uint8_t *) dst, (const uint8_t *) src, rows,
-                                                    cols, dst_stride, src_stride, vec_ok);
-        KSP_CHECK_LAUNCH();
-        return 0;
+        // region [r_lo, rows) x [c_lo, cols) of the source
+        auto rest = [&](int64_t r_lo, int64_t c_lo, int64_t r_hi, int64_t c_hi) -> int {
+            if (r_hi <= r_lo || c_hi <= c_lo) return 0;
+            dim3 grid((unsigned) ksp_divup(c_hi - c_lo, 64), (unsigned) ksp_divup(r_hi - r_lo, 64));
+            if (grid.y > 65535) return KSP_ETOOLARGE;
+            transpose_bytes_kernel<<<grid, 256, 0, s>>>(
+                (uint8_t *) dst + c_lo * dst_stride + r_lo, (const uint8_t *) src + r_lo * src_stride + c_lo,
+                r_hi - r_lo, c_hi - c_lo, dst_stride, src_stride, vec_ok && r_lo % 4 == 0 && c_lo % 4 == 0);
+            KSP_CHECK_LAUNCH();
+            return 0;
+        };
+        if (r_main > 0 && c_main > 0) {
+            int rc = rest(0, c_main, r_main, cols);            // right strip
+            if (rc) return rc;
+            return rest(r_main, 0, rows, cols);                // bottom strip (full width)
+        }
+        return rest(0, 0, rows, cols);
     }
     case 2: return launch_tile<uint16_t>(s, dst, src, rows, cols, dst_stride, src_stride);
     case 4: return launch_tile<uint32_t>(s, dst, src, rows, cols, dst_stride, src_stride);

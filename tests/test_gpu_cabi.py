@@ -51,6 +51,25 @@ def test_transpose_bytes_vector_path():
     np.testing.assert_array_equal(a.T, cu.transpose(a, 4, 8))
 
 
+@pytest.mark.parametrize("shape,pads", [((256, 384), (0, 0)), ((300, 500), (0, 0)), ((128, 128), (16, 32)),
+                                        ((391, 130), (9, 2)), ((1024, 640), (0, 16)), ((640, 1), (0, 0))])
+def test_transpose_bytes_128bit_tiles(shape, pads):
+    """uint8 arrays with 16-byte aligned rows take the 128 x 128-tile kernel for the whole tiles and
+    the 64 x 64 one for the ragged strips; misaligned ones take the latter throughout."""
+    rs = np.random.RandomState(3)
+    a = rs.randint(0, 256, shape).astype(np.uint8)
+    np.testing.assert_array_equal(a.T, cu.transpose(a, *pads))
+
+
+def test_transpose_rejects_bad_element_size():
+    from ctypes import c_void_p
+
+    from katsdpsigproc_b200 import _capi
+    lib = _capi.load()
+    for size in (0, 3, 32):
+        assert lib.ksp_transpose(None, c_void_p(256), c_void_p(512), 4, 4, 4, 4, size) == -1
+
+
 # ------------------------------------------------------------------ background
 def bg_inputs(channels, baselines, seed=1):
     rs = np.random.RandomState(seed)

@@ -77,6 +77,10 @@ def full(path):
     hdr, units, data = rows[0], rows[1], rows[2:]
     ki = hdr.index("Kernel Name")
     cols = [(k, hdr.index(k)) for k in KEYS if k in hdr]
+    # instructions per pipe (ALU / FMA / LSU / XU ...) and pipe utilisation, whatever this ncu calls them
+    cols += [(k, i) for i, k in enumerate(hdr)
+             if re.search(r"inst_executed_pipe_[a-z_]+\.(sum|avg\.pct_of_peak_sustained_active)$", k)
+             and not re.search(r"_pred_|_op_|tensor|_fp64|fp16|tma|tmem|uniform_|ipa|tex", k)]
     seen = collections.OrderedDict()
     for r in data:
         seen.setdefault((short(r[ki]), r[hdr.index("Grid Size")]), r)   # first launch of each shape

@@ -42,6 +42,10 @@ def main():
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--chunks", type=str, default="0")
     ap.add_argument("--only-fused", action="store_true")
+    ap.add_argument("--sweep", action="store_true",
+                    help="also the helper configurations of BASELINE.json configs[2], [3]: Percentile5 "
+                         "over 8320 rows x 256..65536 columns, complex64 transpose 3072 x 8320")
+    ap.add_argument("--dataflow", action="store_true", help="also the dataflow form of the flagger")
     ap.add_argument("--tpad", type=int, default=0,
                     help="extra elements in the row stride of the baseline-major arrays")
     args = ap.parse_args()
@@ -101,7 +105,7 @@ def main():
         rec("transpose_u8", timeit(lambda: _capi.call(
             "ksp_transpose", S, p(flags), p(flags_t), B, C, B, CT, 1), args.reps, flush), 2)
     print("flagged fraction", float(flags.float().mean()))
-    for chunk in [int(x) for x in args.chunks.split(",")]:
+    for chunk in [int(x) for x in args.chunks.split(",")] + ([-1] if args.dataflow else []):
         prm = cu.flagger_params(C, B, B, B, n_windows=7, chunk_baselines=chunk)
         nbytes = _capi.load().ksp_flagger_scratch_bytes(byref(prm))
         used = _capi.load().ksp_flagger_chunk_baselines(byref(prm))
@@ -134,6 +138,27 @@ def main():
         dest = torch.empty(B, 2, dtype=torch.float32, device=dev)
         rec("maskedsum_c64", timeit(lambda: _capi.call(
             "ksp_maskedsum", S, p(vis), p(mask), p(dest), C, B, B, 0, 0), args.reps, flush), 8)
+    if args.sweep:
+        del dev_cm, dev_t, flags_t
+        torch.cuda.empty_cache()
+        rows = B
+        for cols in (256, 1024, 4096, 16384, 65536):
+            src = torch.randn(rows, cols, device=dev, dtype=torch.float32).abs_()
+            pct = torch.empty(5, rows, dtype=torch.float32, device=dev)
+            ms = timeit(lambda: _capi.call("ksp_percentile5", S, p(src), p(pct), rows, cols, rows, 0, cols, 1, 0),
+                        args.reps, flush)
+            res[f"percentile5_f32_{rows}x{cols}"] = {"ms": round(ms, 4),
+                                                     "GB/s": round(4 * rows * cols / ms / 1e6, 1)}
+            print(f"percentile5_f32_{rows}x{cols}", res[f"percentile5_f32_{rows}x{cols}"], flush=True)
+            ms = timeit(lambda: _capi.call("ksp_madnz_t", S, p(src), p(pct), cols, rows, cols), args.reps, flush)
+            res[f"madnz_t_{rows}x{cols}"] = {"ms": round(ms, 4), "GB/s": round(4 * rows * cols / ms / 1e6, 1)}
+            print(f"madnz_t_{rows}x{cols}", res[f"madnz_t_{rows}x{cols}"], flush=True)
+            del src, pct
+        a64 = torch.randn(3072, B, 2, device=dev, dtype=torch.float32)
+        b64 = torch.empty(B, 3072, 2, device=dev, dtype=torch.float32)
+        ms = timeit(lambda: _capi.call("ksp_transpose", S, p(b64), p(a64), 3072, B, 3072, B, 8), args.reps, flush)
+        res["transpose_c64_3072x8320"] = {"ms": round(ms, 4), "GB/s": round(16 * 3072 * B / ms / 1e6, 1)}
+        print("transpose_c64_3072x8320", res["transpose_c64_3072x8320"], flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     with open(os.environ.get("TK_OUT", "gpurun_out/time_kernels.json"), "w") as f:
         json.dump({"channels": C, "baselines": B, "results": res}, f, indent=1)
