@@ -142,6 +142,8 @@ class BackgroundMedianFilterDeviceTemplate(FixedTuning, AbstractBackgroundDevice
         ``KATSDPSIGPROC_B200_ABS_MODE``)
     """
 
+    host_class = host.ReferenceHostClass("BackgroundMedianFilterHost")   # reference rfi/device.py: same attribute
+
     _TUNING = {"wgs": 128, "csplit": 4}
 
     def __init__(self, context: Any, width: int, is_amplitude: bool = False,
@@ -234,6 +236,8 @@ class NoiseEstHostFromDevice(host.AbstractNoiseEstHost):
 class NoiseEstMADDeviceTemplate(FixedTuning, AbstractNoiseEstDeviceTemplate):
     """``noise = 1.4826 * median(|deviations| != 0)`` per baseline, channel-major input."""
 
+    host_class = host.ReferenceHostClass("NoiseEstMADHost")   # reference rfi/device.py: same attribute
+
     transposed = False
     _TUNING = {"wgsx": 32, "wgsy": 32}
 
@@ -276,6 +280,8 @@ class NoiseEstMADTDeviceTemplate(FixedTuning, AbstractNoiseEstDeviceTemplate):
     where it sizes a register array; here any channel count up to it works, and rows
     longer than 49 152 channels fall back from shared memory to L2.
     """
+
+    host_class = host.ReferenceHostClass("NoiseEstMADHost")   # reference rfi/device.py: same attribute
 
     transposed = True
     _TUNING = {"wgsx": 1024}
@@ -349,6 +355,8 @@ class ThresholdHostFromDevice(host.AbstractThresholdHost):
 class ThresholdSimpleDeviceTemplate(FixedTuning, AbstractThresholdDeviceTemplate):
     """``flag = deviation > n_sigma * noise[baseline]``, either memory order."""
 
+    host_class = host.ReferenceHostClass("ThresholdSimpleHost")   # reference rfi/device.py: same attribute
+
     _TUNING = {"wgsx": 256, "wgsy": 1}
 
     def __init__(self, context: Any, transposed: bool, flag_value: int = 1,
@@ -407,6 +415,8 @@ class ThresholdSumDeviceTemplate(FixedTuning, AbstractThresholdDeviceTemplate):
     Takes transposed (baseline-major) data.  ``n_windows`` is at most 11 (windows up to 1024);
     up to 7 (windows up to 64) run on the fast kernel.
     """
+
+    host_class = host.ReferenceHostClass("ThresholdSumHost")   # reference rfi/device.py: same attribute
 
     transposed = True
     _TUNING = {"wgs": 1024, "vt": 32}

@@ -37,3 +37,31 @@ class AbstractFlaggerHost(ABC):
     @abstractmethod
     def __call__(self, vis: np.ndarray, input_flags: Optional[np.ndarray] = None) -> np.ndarray:
         """uint8 flags (channels x baselines) for complex visibilities."""
+
+
+class ReferenceHostClass:
+    """Descriptor behind ``Template.host_class`` (reference ``rfi/device.py:174,380,504,679,834``).
+
+    In the reference every device template names the numpy class that computes the same thing on
+    the CPU, and the reference's own device tests build their expected values with
+    ``template.host_class(...)`` (``test/rfi/test_background.py:89``, ``test_noise_est.py:57``,
+    ``test_threshold.py:65``).  This package ships no CPU implementation, so the attribute
+    resolves, on access, to the class of that name in the REFERENCE package
+    (``katsdpsigproc.rfi.host``) when it can be imported - the situation of somebody re-pointing
+    the reference's tests at this package, or of this repository's tests, which put the
+    reference's own module on the path - and raises ``ImportError`` otherwise.  Nothing on the
+    device path ever touches it.
+    """
+
+    def __init__(self, name: str) -> None:
+        self.name = name
+
+    def __get__(self, obj: object, owner: type) -> type:
+        try:
+            from katsdpsigproc.rfi import host as reference_host
+        except ImportError as exc:
+            raise ImportError(
+                f"host_class is the reference's katsdpsigproc.rfi.host.{self.name}: install the "
+                "reference package (or put it on sys.path) to use it; katsdpsigproc_b200 has no "
+                "CPU implementation") from exc
+        return getattr(reference_host, self.name)

@@ -227,3 +227,33 @@ def test_backend_implements_the_abstract_interfaces():
                                 (cuda.CommandQueue, abc.AbstractCommandQueue)):
         assert issubclass(concrete, interface)
         assert not getattr(concrete, "__abstractmethods__", None), concrete.__abstractmethods__
+
+
+def test_host_class_resolves_to_the_reference(context):
+    """``Template.host_class`` (reference rfi/device.py:174,380,504,679,834): the reference's own
+    host classes when katsdpsigproc.rfi.host is importable, ImportError (not a silent CPU
+    substitute) when it is not."""
+    import sys
+
+    import oracle
+    templates = [
+        (rfi.BackgroundMedianFilterDeviceTemplate(context, 13), "BackgroundMedianFilterHost"),
+        (rfi.NoiseEstMADDeviceTemplate(context), "NoiseEstMADHost"),
+        (rfi.NoiseEstMADTDeviceTemplate(context, 4096), "NoiseEstMADHost"),
+        (rfi.ThresholdSimpleDeviceTemplate(context, False), "ThresholdSimpleHost"),
+        (rfi.ThresholdSumDeviceTemplate(context), "ThresholdSumHost"),
+    ]
+    ref = oracle.reference_host()
+    if ref is not None:
+        for template, name in templates:
+            assert template.host_class is getattr(ref, name)
+            assert type(template).host_class is getattr(ref, name)
+        assert templates[0][0].host_class(5, True)(np.ones((7, 2), np.float32)).shape == (7, 2)
+    else:
+        saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.startswith("katsdpsigproc.")
+                 or k == "katsdpsigproc"}
+        try:
+            with pytest.raises(ImportError):
+                templates[0][0].host_class
+        finally:
+            sys.modules.update(saved)

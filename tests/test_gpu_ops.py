@@ -162,6 +162,65 @@ def test_threshold_sum(context, command_queue, n_windows):
     assert int((host != out).sum()) <= near.get("band", 0)
 
 
+# ----------------------------------------------------------------------------- host_class
+# The reference's own device tests, written as they are written there: the expected value comes
+# from ``template.host_class(...)`` (test/rfi/test_background.py:78-104, test_noise_est.py:54-61,
+# test_threshold.py:60-70).  host_class resolves to the reference's katsdpsigproc.rfi.host, which
+# oracle/_ref holds in the build container and on the GPU box (oracle/make_ref.py).
+@pytest.fixture
+def reference_on_path():
+    import oracle
+    if oracle.reference_host() is None:
+        pytest.skip("oracle/_ref (the reference's rfi/host.py) is not present")
+
+
+@pytest.mark.parametrize("amplitudes", [False, True])
+@pytest.mark.parametrize("use_flags", list(rfi.BackgroundFlags))
+def test_reference_background_test(context, command_queue, abs_mode, reference_on_path, amplitudes, use_flags):
+    width = 5
+    rs = np.random.RandomState(seed=1)                      # as _make_vis / _make_flags there
+    vis = (rs.standard_normal((417, 313)) + rs.standard_normal((417, 313)) * 1j).astype(np.complex64)
+    flags = (rs.random_sample((417, 313)) < 0.1).astype(np.uint8)
+    flags[:, 3] = 1
+    flags[100:110, :] = 1
+    flags *= rs.randint(1, 256, flags.shape).astype(np.uint8)
+    if amplitudes:
+        vis = np.abs(vis)
+    if use_flags is rfi.BackgroundFlags.CHANNEL:
+        flags = flags[:, 0].copy()
+    elif use_flags is rfi.BackgroundFlags.NONE:
+        flags = None
+    template = rfi.BackgroundMedianFilterDeviceTemplate(context, width, amplitudes, use_flags,
+                                                        abs_mode=abs_mode)
+    bg_host = template.host_class(width, amplitudes)
+    bg_device = rfi.BackgroundHostFromDevice(template, command_queue)
+    full = None if flags is None else (flags if flags.ndim == 2 else np.repeat(flags[:, None], 313, 1))
+    expected = bg_host(vis, full)
+    np.testing.assert_allclose(expected, bg_device(vis, flags), atol=1e-6)
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_reference_noise_est_test(context, command_queue, reference_on_path, transposed):
+    rs = np.random.RandomState(seed=1)
+    deviations = rs.standard_normal((117, 273)).astype(np.float32)
+    template = (rfi.NoiseEstMADTDeviceTemplate(context, 10240) if transposed
+                else rfi.NoiseEstMADDeviceTemplate(context))
+    ne_host = template.host_class()
+    ne_device = rfi.NoiseEstHostFromDevice(template, command_queue)
+    np.testing.assert_allclose(ne_host(deviations), ne_device(deviations), rtol=2e-7)
+
+
+@pytest.mark.parametrize("kind", ["simple", "simple_t", "sum"])
+def test_reference_threshold_test(context, command_queue, reference_on_path, kind):
+    deviations, noise = threshold_case()
+    template = {"simple": lambda: rfi.ThresholdSimpleDeviceTemplate(context, False),
+                "simple_t": lambda: rfi.ThresholdSimpleDeviceTemplate(context, True),
+                "sum": lambda: rfi.ThresholdSumDeviceTemplate(context)}[kind]()
+    th_host = template.host_class(11.0)
+    th_device = rfi.ThresholdHostFromDevice(template, command_queue, 11.0)
+    np.testing.assert_equal(th_host(deviations, noise), th_device(deviations, noise))
+
+
 # ----------------------------------------------------------------------------- flagger
 def flagger_case(channels=117, baselines=131):
     rs = np.random.RandomState(1)
