@@ -63,6 +63,8 @@ const char *ksp_error_string(int code);
  * ---------------------------------------------------------------------- */
 int ksp_device_count(int *count);                                   /* cuda.py:152-155 */
 int ksp_device_name(int device, char *buf, int buf_len);            /* cuda.py:98-100 */
+int ksp_device_pci_bus_id(int device, char *buf, int buf_len);      /* "0000:1b:00.0"; names the SAME GPU to
+                                                                     * NVML, whose indices ignore CUDA_VISIBLE_DEVICES */
 int ksp_device_attributes(int device, int *cc_major, int *cc_minor, int *sm_count,
                           int *warp_size, size_t *total_mem, int *l2_bytes); /* :134-141 */
 int ksp_device_set(int device);                                     /* Context.__enter__ :243-245 */
@@ -94,9 +96,6 @@ int ksp_memcpy_2d_async(void *dst, size_t dst_pitch, const void *src, size_t src
                                                                     /* enqueue_*_buffer_rect :299-431 */
 int ksp_memset_async(void *dst, int value, size_t bytes, void *stream); /* enqueue_zero_buffer :433-440 */
 
-/* L2 persistence window for the flagger's scratch (no reference equivalent;
- * bytes == 0 clears it). */
-int ksp_stream_set_l2_window(void *stream, void *base, size_t bytes, float hit_ratio);
 
 /* ------------------------------------------------------------------------
  * Kernels

@@ -58,6 +58,7 @@ PROTOTYPES = {
     "ksp_abi_version": (c_int, []),
     "ksp_error_string": (c_char_p, [c_int]),
     "ksp_device_count": (c_int, [POINTER(c_int)]),
+    "ksp_device_pci_bus_id": (c_int, [c_int, ctypes.c_char_p, c_int]),
     "ksp_device_name": (c_int, [c_int, c_char_p, c_int]),
     "ksp_device_attributes": (
         c_int,
@@ -87,7 +88,6 @@ PROTOTYPES = {
         [c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_size_t, c_int, c_void_p],
     ),
     "ksp_memset_async": (c_int, [c_void_p, c_int, c_size_t, c_void_p]),
-    "ksp_stream_set_l2_window": (c_int, [c_void_p, c_void_p, c_size_t, c_float]),
     "ksp_transpose": (
         c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int64, c_int64, c_int]),
     "ksp_background_median_filter": (

@@ -47,6 +47,13 @@ int ksp_device_name(int device, char *buf, int buf_len)
     return 0;
 }
 
+int ksp_device_pci_bus_id(int device, char *buf, int buf_len)
+{
+    if (!buf || buf_len < 13) return KSP_EINVAL;
+    KSP_CUDA(cudaDeviceGetPCIBusId(buf, buf_len, device));
+    return 0;
+}
+
 int ksp_device_attributes(int device, int *cc_major, int *cc_minor, int *sm_count, int *warp_size,
                           size_t *total_mem, int *l2_bytes)
 {
@@ -162,24 +169,6 @@ int ksp_memset_async(void *dst, int value, size_t bytes, void *stream)
 {
     if (bytes == 0) return 0;
     return (int) cudaMemsetAsync(dst, value, bytes, (cudaStream_t) stream);
-}
-
-int ksp_stream_set_l2_window(void *stream, void *base, size_t bytes, float hit_ratio)
-{
-    cudaStreamAttrValue attr;
-    memset(&attr, 0, sizeof(attr));
-    if (bytes) {
-        int dev, max_window = 0;
-        KSP_CUDA(cudaGetDevice(&dev));
-        KSP_CUDA(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev));
-        if ((size_t) max_window < bytes) bytes = (size_t) max_window;
-        attr.accessPolicyWindow.base_ptr = base;
-        attr.accessPolicyWindow.num_bytes = bytes;
-        attr.accessPolicyWindow.hitRatio = hit_ratio;
-        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    }
-    return (int) cudaStreamSetAttribute((cudaStream_t) stream, cudaStreamAttributeAccessPolicyWindow, &attr);
 }
 
 }  // extern "C"

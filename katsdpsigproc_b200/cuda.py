@@ -284,18 +284,22 @@ class CommandQueue(AbstractCommandQueue):
     def enqueue_read_buffer(self, buffer: DeviceBuffer, data: np.ndarray, blocking: bool = True
                             ) -> None:
         """Device -> host copy of the whole buffer."""
+        if data.nbytes != buffer.nbytes:
+            raise ValueError(f"host array has {data.nbytes} bytes, the buffer {buffer.nbytes}")
         self._current()
         _capi.call("ksp_memcpy_async", c_void_p(self._host_ptr(data)), c_void_p(buffer.ptr),
-                   c_size_t(min(buffer.nbytes, data.nbytes)), _capi.D2H, c_void_p(self._stream))
+                   c_size_t(buffer.nbytes), _capi.D2H, c_void_p(self._stream))
         if blocking:
             self.finish()
 
     def enqueue_write_buffer(self, buffer: DeviceBuffer, data: np.ndarray, blocking: bool = True
                              ) -> None:
         """Host -> device copy of the whole buffer."""
+        if data.nbytes != buffer.nbytes:
+            raise ValueError(f"host array has {data.nbytes} bytes, the buffer {buffer.nbytes}")
         self._current()
         _capi.call("ksp_memcpy_async", c_void_p(buffer.ptr), c_void_p(self._host_ptr(data)),
-                   c_size_t(min(buffer.nbytes, data.nbytes)), _capi.H2D, c_void_p(self._stream))
+                   c_size_t(buffer.nbytes), _capi.H2D, c_void_p(self._stream))
         if blocking:
             self.finish()
 

@@ -79,7 +79,7 @@ def shard_sizes(baselines: int, world_size: int, align: int = 32) -> Sequence[in
 
 
 def bind_to_device_locality(device_index: int) -> Optional[List[int]]:
-    """Pin the calling process to the CPUs that are closest to GPU ``device_index``.
+    """Pin the calling process to the CPUs that are closest to CUDA device ``device_index``.
 
     With one process per GPU, the pinned staging buffers of
     :class:`~katsdpsigproc_b200.streaming.StreamingFlagger` are then allocated (first touch)
@@ -94,9 +94,17 @@ def bind_to_device_locality(device_index: int) -> Optional[List[int]]:
     try:
         import pynvml
 
+        import ctypes
+
+        from . import _capi
+
+        # NVML numbers the GPUs of the machine, CUDA those this process may see
+        # (CUDA_VISIBLE_DEVICES): name the device by its PCI bus id, which both agree on
+        bus_id = ctypes.create_string_buffer(32)
+        _capi.call("ksp_device_pci_bus_id", int(device_index), bus_id, len(bus_id))
         pynvml.nvmlInit()
         try:
-            handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+            handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus_id.value)
             words = -(-(os.cpu_count() or 1) // 64)
             mask = pynvml.nvmlDeviceGetCpuAffinity(handle, words)
         finally:
