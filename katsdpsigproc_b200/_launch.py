@@ -24,21 +24,19 @@ def launch(command_queue: Any, name: str, *args: Any) -> None:
 
 
 class FixedTuning:
-    """Mixin for templates: keeps the reference's ``tuning=`` / ``autotune`` surface.
+    """Mixin for templates: the reference's ``tuning=`` / ``autotune`` surface.
 
     The reference searches work-group shapes at run time and caches them in sqlite
     (``tune.py:254-334``).  These kernels target one chip (sm_100a) and pick their launch
-    geometry inside the library from the problem size and the SM count, so ``autotune``
-    returns a fixed dictionary and a user-supplied ``tuning`` mapping is accepted and kept
-    (``template.tuning``) but has no effect on the launch.
+    geometry inside the library from the problem size and the SM count, so every template's
+    ``autotune`` classmethod - same name, same arguments as the reference's, decorated with
+    :func:`katsdpsigproc_b200.tune.autotuner` and therefore cached in the same database layout -
+    returns at once with a fixed dictionary, and a user-supplied ``tuning`` mapping is accepted
+    and kept (``template.tuning``) but has no effect on the launch.
     """
 
     autotune_version = 1
     _TUNING: Mapping[str, Any] = {}
 
-    @classmethod
-    def autotune(cls, context: Any, *args: Any, **kwargs: Any) -> Mapping[str, Any]:
-        return dict(cls._TUNING)
-
-    def _init_tuning(self, context: Any, tuning: Optional[Mapping[str, Any]]) -> None:
-        self.tuning = dict(self.autotune(context) if tuning is None else tuning)
+    def _init_tuning(self, context: Any, tuning: Optional[Mapping[str, Any]], *key: Any) -> None:
+        self.tuning = dict(self.autotune(context, *key) if tuning is None else tuning)

@@ -8,6 +8,7 @@ from typing import Any, Mapping, Optional, Tuple
 import numpy as np
 
 from . import accel
+from . import tune
 from ._launch import FixedTuning, launch, ptr
 
 
@@ -21,6 +22,13 @@ class FillTemplate(FixedTuning):
 
     _TUNING = {"wgs": 256}
 
+    @classmethod
+    @tune.autotuner(test={"wgs": 256})
+    def autotune(cls, context: Any, dtype: Any, ctype: str) -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, dtype: Any, ctype: str,
                  tuning: Optional[Mapping[str, Any]] = None) -> None:
         self.context = context
@@ -28,7 +36,7 @@ class FillTemplate(FixedTuning):
         self.ctype = ctype
         if self.dtype.itemsize not in (1, 2, 4, 8, 16):
             raise ValueError("Fill supports element sizes of 1, 2, 4, 8 and 16 bytes")
-        self._init_tuning(context, tuning)
+        self._init_tuning(context, tuning, self.dtype, ctype)
 
     def instantiate(self, command_queue: Any, shape: Tuple[int, ...],
                     allocator: Optional[accel.AbstractAllocator] = None) -> "Fill":

@@ -7,6 +7,7 @@ from typing import Any, Mapping, Optional, Tuple
 import numpy as np
 
 from . import _capi, accel
+from . import tune
 from ._launch import FixedTuning, launch, ptr
 
 
@@ -19,13 +20,20 @@ class MaskedSumTemplate(FixedTuning):
 
     _TUNING = {"size": 16}
 
+    @classmethod
+    @tune.autotuner(test={"size": 16})
+    def autotune(cls, context: Any, use_amplitudes: bool) -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, use_amplitudes: bool = False,
                  tuning: Optional[Mapping[str, Any]] = None,
                  abs_mode: Optional[int] = None) -> None:
         self.context = context
         self.use_amplitudes = use_amplitudes
         self.abs_mode = _capi.default_abs_mode() if abs_mode is None else abs_mode
-        self._init_tuning(context, tuning)
+        self._init_tuning(context, tuning, use_amplitudes)
 
     def instantiate(self, command_queue: Any, shape: Tuple[int, int],
                     allocator: Optional[accel.AbstractAllocator] = None) -> "MaskedSum":

@@ -7,6 +7,7 @@ from typing import Any, Mapping, Optional, Tuple
 import numpy as np
 
 from . import _capi, accel
+from . import tune
 from ._launch import FixedTuning, launch, ptr
 
 
@@ -35,6 +36,13 @@ class Percentile5Template(FixedTuning):
 
     _TUNING = {"size": 1024, "wgsy": 1}
 
+    @classmethod
+    @tune.autotuner(test={"size": 1024, "wgsy": 1})
+    def autotune(cls, context: Any, max_columns: int, is_amplitude: bool) -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, max_columns: int, is_amplitude: bool = True,
                  tuning: Optional[Mapping[str, Any]] = None,
                  abs_mode: Optional[int] = None) -> None:
@@ -42,7 +50,7 @@ class Percentile5Template(FixedTuning):
         self.max_columns = max_columns
         self.is_amplitude = is_amplitude
         self.abs_mode = _capi.default_abs_mode() if abs_mode is None else abs_mode
-        self._init_tuning(context, tuning)
+        self._init_tuning(context, tuning, max_columns, is_amplitude)
 
     def instantiate(self, command_queue: Any, shape: Tuple[int, int],
                     column_range: Optional[Tuple[int, int]] = None,

@@ -9,6 +9,7 @@ from typing import Any, Mapping, Optional, Tuple
 import numpy as np
 
 from . import _capi, accel
+from . import tune
 from ._launch import FixedTuning, launch, ptr
 
 
@@ -24,6 +25,13 @@ class HReduceTemplate(FixedTuning):
 
     _TUNING = {"wgsx": 32, "wgsy": 8}
 
+    @classmethod
+    @tune.autotuner(test={"wgsx": 32, "wgsy": 8})
+    def autotune(cls, context: Any, dtype: Any, ctype: str, op: str, identity: str, extra_code: str) -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, dtype: Any, ctype: str, op: str, identity: str,
                  extra_code: str = "", tuning: Optional[Mapping[str, Any]] = None) -> None:
         self.context = context
@@ -32,7 +40,7 @@ class HReduceTemplate(FixedTuning):
         self.op = op
         self.identity = identity
         self.extra_code = extra_code
-        self._init_tuning(context, tuning)
+        self._init_tuning(context, tuning, self.dtype, ctype, op, identity, extra_code)
         self.wgsx = self.tuning["wgsx"]
         self.wgsy = self.tuning["wgsy"]
         context._make_current()

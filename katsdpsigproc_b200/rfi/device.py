@@ -35,7 +35,7 @@ from typing import Any, List, Mapping, Optional, Tuple, Union
 
 import numpy as np
 
-from .. import _capi, accel, transpose
+from .. import _capi, accel, transpose, tune
 from .._launch import FixedTuning, launch, ptr
 from . import host
 
@@ -146,6 +146,13 @@ class BackgroundMedianFilterDeviceTemplate(FixedTuning, AbstractBackgroundDevice
 
     _TUNING = {"wgs": 128, "csplit": 4}
 
+    @classmethod
+    @tune.autotuner(test={"wgs": 128, "csplit": 4})
+    def autotune(cls, context: Any, width: int, is_amplitude: bool, use_flags: "BackgroundFlags") -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, width: int, is_amplitude: bool = False,
                  use_flags: Union[BackgroundFlags, bool] = BackgroundFlags.NONE,
                  tuning: Optional[Mapping[str, Any]] = None,
@@ -165,7 +172,7 @@ class BackgroundMedianFilterDeviceTemplate(FixedTuning, AbstractBackgroundDevice
         self.is_amplitude = is_amplitude
         self.use_flags = use_flags
         self.abs_mode = _capi.default_abs_mode() if abs_mode is None else abs_mode
-        self._init_tuning(context, tuning)
+        self._init_tuning(context, tuning, width, is_amplitude, use_flags)
 
     def instantiate(self, command_queue: Any, channels: int, baselines: int,
                     allocator: Optional[accel.AbstractAllocator] = None
@@ -241,6 +248,13 @@ class NoiseEstMADDeviceTemplate(FixedTuning, AbstractNoiseEstDeviceTemplate):
     transposed = False
     _TUNING = {"wgsx": 32, "wgsy": 32}
 
+    @classmethod
+    @tune.autotuner(test={"wgsx": 32, "wgsy": 32})
+    def autotune(cls, context: Any) -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, tuning: Optional[Mapping[str, Any]] = None) -> None:
         self.context = context
         self._init_tuning(context, tuning)
@@ -286,11 +300,18 @@ class NoiseEstMADTDeviceTemplate(FixedTuning, AbstractNoiseEstDeviceTemplate):
     transposed = True
     _TUNING = {"wgsx": 1024}
 
+    @classmethod
+    @tune.autotuner(test={"wgsx": 1024})
+    def autotune(cls, context: Any, max_channels: int) -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, max_channels: int,
                  tuning: Optional[Mapping[str, Any]] = None) -> None:
         self.context = context
         self.max_channels = max_channels
-        self._init_tuning(context, tuning)
+        self._init_tuning(context, tuning, max_channels)
 
     def instantiate(self, command_queue: Any, channels: int, baselines: int,
                     allocator: Optional[accel.AbstractAllocator] = None) -> "NoiseEstMADTDevice":
@@ -359,6 +380,13 @@ class ThresholdSimpleDeviceTemplate(FixedTuning, AbstractThresholdDeviceTemplate
 
     _TUNING = {"wgsx": 256, "wgsy": 1}
 
+    @classmethod
+    @tune.autotuner(test={"wgsx": 256, "wgsy": 1})
+    def autotune(cls, context: Any) -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, transposed: bool, flag_value: int = 1,
                  tuning: Optional[Mapping[str, Any]] = None) -> None:
         self.context = context
@@ -421,6 +449,13 @@ class ThresholdSumDeviceTemplate(FixedTuning, AbstractThresholdDeviceTemplate):
     transposed = True
     _TUNING = {"wgs": 1024, "vt": 32}
 
+    @classmethod
+    @tune.autotuner(test={"wgs": 1024, "vt": 32})
+    def autotune(cls, context: Any, n_windows: int) -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, n_windows: int = 4, flag_value: int = 1,
                  tuning: Optional[Mapping[str, Any]] = None) -> None:
         if n_windows < 1:
@@ -430,7 +465,7 @@ class ThresholdSumDeviceTemplate(FixedTuning, AbstractThresholdDeviceTemplate):
         self.context = context
         self.n_windows = n_windows
         self.flag_value = flag_value
-        self._init_tuning(context, tuning)
+        self._init_tuning(context, tuning, n_windows)
 
     def instantiate(self, command_queue: Any, channels: int, baselines: int, n_sigma: float,
                     threshold_falloff: float = DEFAULT_THRESHOLD_FALLOFF,

@@ -7,6 +7,7 @@ from typing import Any, Mapping, Optional, Tuple
 import numpy as np
 
 from . import accel
+from . import tune
 from ._launch import FixedTuning, launch, ptr
 
 
@@ -28,6 +29,13 @@ class TransposeTemplate(FixedTuning):
 
     _TUNING = {"block": 32, "vtx": 1, "vty": 4}
 
+    @classmethod
+    @tune.autotuner(test={"block": 32, "vtx": 1, "vty": 4})
+    def autotune(cls, context: Any, dtype: Any, ctype: str) -> Mapping[str, Any]:
+        """Nothing to search (the library fixes the launch geometry for sm_100a); the answer
+        is cached under the reference's key layout all the same (see :mod:`katsdpsigproc_b200.tune`)."""
+        return dict(cls._TUNING)
+
     def __init__(self, context: Any, dtype: Any, ctype: str = "",
                  tuning: Optional[Mapping[str, Any]] = None) -> None:
         self.context = context
@@ -35,7 +43,7 @@ class TransposeTemplate(FixedTuning):
         self.ctype = ctype
         if self.dtype.itemsize not in (1, 2, 4, 8, 16):
             raise ValueError("element size must be 1, 2, 4, 8 or 16 bytes")
-        self._init_tuning(context, tuning)
+        self._init_tuning(context, tuning, self.dtype, ctype)
 
     def instantiate(self, command_queue: Any, shape: Tuple[int, int],
                     allocator: Optional[accel.AbstractAllocator] = None) -> "Transpose":

@@ -16,8 +16,18 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# fixtures, --devices and the markers of the reference's plugin (device / force_autotune / ...)
+pytest_plugins = ["katsdpsigproc_b200.pytest_plugin"]
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: test needs a CUDA device (B200)")
+
+
+@pytest.fixture(autouse=True)
+def _stub_autotune(patch_autotune):
+    """As in the reference's suite: templates take their ``test=`` tuning instead of consulting
+    the sqlite cache, unless the test is marked ``force_autotune``."""
 
 
 @pytest.fixture(scope="session")
