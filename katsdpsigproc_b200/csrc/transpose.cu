@@ -12,6 +12,7 @@
 //     64x64-element tile moved as 32-bit words (16 lanes per 64-byte row), and
 //     re-packed from shared memory so that the stores are 32-bit words too.
 #include "common.cuh"
+#include "../../include/ksp_transpose_base.cuh"
 
 namespace {
 
@@ -134,6 +135,42 @@ transpose_bytes128_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__
         __stcs(reinterpret_cast<uint4 *>(out + k * dst_stride), make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]));
 }
 
+// Plain transposition written with the fusable tools of include/ksp_transpose_base.cuh (the
+// reference's transpose.mako:44-73 is the same metakernel with these two bodies); used for the
+// element sizes off the flagger's path (2 and 16 bytes).
+template <typename T, int BLOCK, int VTX, int VTY>
+__global__ void __launch_bounds__(BLOCK * BLOCK)
+transpose_base_kernel(T *__restrict__ out, const T *__restrict__ in, int in_rows, int in_cols,
+                      int64_t out_stride, int64_t in_stride)
+{
+    using Tile = ksp::TransposeTile<T, BLOCK, VTX, VTY>;
+    __shared__ typename Tile::Values values;
+    typename Tile::Coords at;
+    Tile::init_simple(at);
+    Tile::load(at, [&](int r, int c, int lr, int lc) {
+        if (r < in_rows && c < in_cols) values.arr[lr][lc] = in[r * in_stride + c];
+    });
+    __syncthreads();
+    Tile::store(at, [&](int r, int c, int lr, int lc) {
+        if (r < in_cols && c < in_rows) out[r * out_stride + c] = values.arr[lr][lc];
+    });
+}
+
+template <typename T>
+int launch_base(cudaStream_t s, void *dst, const void *src, int64_t rows, int64_t cols,
+                int64_t dst_stride, int64_t src_stride)
+{
+    constexpr int BLOCK = 16, VTX = 2, VTY = 2;
+    using Tile = ksp::TransposeTile<T, BLOCK, VTX, VTY>;
+    if (rows > 0x7fffffff || cols > 0x7fffffff) return KSP_ETOOLARGE;
+    dim3 grid((unsigned) ksp_divup(cols, Tile::COLS), (unsigned) ksp_divup(rows, Tile::ROWS));
+    if (grid.y > 65535) return KSP_ETOOLARGE;
+    transpose_base_kernel<T, BLOCK, VTX, VTY><<<grid, dim3(BLOCK, BLOCK), 0, s>>>(
+        (T *) dst, (const T *) src, (int) rows, (int) cols, dst_stride, src_stride);
+    KSP_CHECK_LAUNCH();
+    return 0;
+}
+
 template <typename T>
 int launch_tile(cudaStream_t s, void *dst, const void *src, int64_t rows, int64_t cols,
                 int64_t dst_stride, int64_t src_stride)
@@ -192,10 +229,10 @@ extern "C" int ksp_transpose(void *stream, void *dst, const void *src, int64_t r
         }
         return rest(0, 0, rows, cols);
     }
-    case 2: return launch_tile<uint16_t>(s, dst, src, rows, cols, dst_stride, src_stride);
+    case 2: return launch_base<uint16_t>(s, dst, src, rows, cols, dst_stride, src_stride);
     case 4: return launch_tile<uint32_t>(s, dst, src, rows, cols, dst_stride, src_stride);
     case 8: return launch_tile<uint2>(s, dst, src, rows, cols, dst_stride, src_stride);
-    case 16: return launch_tile<uint4>(s, dst, src, rows, cols, dst_stride, src_stride);
+    case 16: return launch_base<uint4>(s, dst, src, rows, cols, dst_stride, src_stride);
     default: return KSP_EINVAL;
     }
 }
