@@ -346,6 +346,44 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
         // whole tile inside the array and 16-byte aligned rows: no test per store (block-uniform)
         const bool whole = TRANSPOSED && (b0 + TILE_B <= a.baselines) && (c0 + TC <= C) &&
                            ((a.out_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(a.out) & 15) == 0);
+        if (TRANSPOSED && whole && (TILE_B * RUNS8) % BG_THREADS == 0 && BG_THREADS % (2 * RUNS8) == 0) {
+            // Whole tile, baseline-major output: the thread's runs are BG_THREADS / RUNS8 baseline
+            // rows apart with the same channel offset, so everything that depends on the thread is
+            // computed once and each further run costs two additions (this part of the kernel is
+            // bound by the ALU pipe, which the selection network needs for itself).
+            constexpr int STEP_B = BG_THREADS / RUNS8;            // baseline rows between two runs of a thread
+            const int t = threadIdx.x;
+            const int bl = 2 * (t / (2 * RUNS8)) + (t & 1);       // (see the general loop below)
+            const int j = (t % (2 * RUNS8)) >> 1;
+            const float *src = amp_sm + bl * G::P + 8 * j;
+            float *o = a.out + (b0 + bl + row_off) * a.out_stride + c0 + 8 * j;
+            const int64_t o_step = (int64_t) STEP_B * a.out_stride;
+#pragma unroll
+            for (int k = 0; k < (TILE_B * RUNS8) / BG_THREADS; k++) {
+                float w[24];
+#pragma unroll
+                for (int q4 = 0; q4 < 6; q4++) {
+                    float4 q = *reinterpret_cast<const float4 *>(src + k * STEP_B * G::P + 4 * q4);
+                    w[4 * q4] = q.x; w[4 * q4 + 1] = q.y; w[4 * q4 + 2] = q.z; w[4 * q4 + 3] = q.w;
+                }
+                float e[20];
+#pragma unroll
+                for (int i = 0; i < 20; i++) e[i] = w[i + 2];    // channels c-6 .. c+13
+                float m[8], o8[8];
+                median13x8(e, m);
+#pragma unroll
+                for (int i = 0; i < 8; i++) o8[i] = e[6 + i] - m[i];
+                if (Where::KEEP_IN_L2) {
+                    stg_keep_f4(o, make_float4(o8[0], o8[1], o8[2], o8[3]));
+                    stg_keep_f4(o + 4, make_float4(o8[4], o8[5], o8[6], o8[7]));
+                } else {
+                    reinterpret_cast<float4 *>(o)[0] = make_float4(o8[0], o8[1], o8[2], o8[3]);
+                    reinterpret_cast<float4 *>(o)[1] = make_float4(o8[4], o8[5], o8[6], o8[7]);
+                }
+                o += o_step;
+            }
+            return;
+        }
         for (int t = threadIdx.x; t < TILE_B * RUNS8; t += BG_THREADS) {
             int bl, j;
             if (TRANSPOSED) {

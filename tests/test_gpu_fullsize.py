@@ -121,6 +121,45 @@ def test_cfg5_shard_shape(context, command_queue, abs_mode):
     assert np.all(flags[spikes != 0] == 1)
 
 
+def fast_dump(channels, baselines, seed):
+    """Noise + isolated spikes + narrowband lines like hn.synthetic_vis, from numpy's fast float32
+    generator (a 32768 x 8320 dump in seconds rather than minutes)."""
+    rng = np.random.default_rng(seed)
+    vis = np.empty((channels, baselines), np.complex64)
+    spikes = np.empty((channels, baselines), bool)
+    for c0 in range(0, channels, 2048):
+        n = min(2048, channels - c0)
+        block = vis[c0:c0 + n].view(np.float32).reshape(n, baselines, 2)
+        block[...] = rng.standard_normal((n, baselines, 2), dtype=np.float32)
+        hit = rng.random((n, baselines), dtype=np.float32) < np.float32(1 / 64)
+        hit |= rng.random((n, 1), dtype=np.float32) < np.float32(0.005)
+        amp = rng.random((n, baselines), dtype=np.float32) * np.float32(20) + np.float32(50)
+        phase = rng.random((n, baselines), dtype=np.float32) * np.float32(2 * np.pi)
+        block[..., 0] += hit * amp * np.cos(phase)
+        block[..., 1] += hit * amp * np.sin(phase)
+        spikes[c0:c0 + n] = hit
+    return vis, spikes
+
+
+@pytest.mark.parametrize("baselines", [8320, 1620])
+def test_benchmark_shape_on_the_default_path(context, command_queue, abs_mode, baselines):
+    """The shapes bench.py times, run the way bench.py runs them (FlaggerDeviceTemplate defaults:
+    8320 baselines = chunks of 3 x 2368 + 1216 on 4 lanes; 1620, the 8-GPU shard of the 12960-baseline
+    dump = two launches per stage), with the parity check of SURVEY.md 8(d): a deterministic subset
+    of baselines at the full channel count against the oracle, plus injected RFI recovered."""
+    vis, spikes = fast_dump(32768, baselines, seed=baselines)
+    flags, noise = run_flagger(context, command_queue, vis, abs_mode)
+    idx = set(range(64)) | set(range(0, baselines, 65)) | set(range(baselines - 64, baselines))
+    pick = np.array(sorted(idx))
+    want_flags, _, want_noise = contract.flagger(np.ascontiguousarray(vis[:, pick]), None,
+                                                 n_windows=7, abs_mode=abs_mode)
+    assert np.array_equal(noise[pick].view(np.uint32), want_noise.view(np.uint32))
+    np.testing.assert_array_equal(want_flags, flags[:, pick])
+    assert np.all(flags[spikes] == 1)
+    assert flags.mean() < spikes.mean() + 0.001
+    assert np.all(np.isfinite(noise)) and noise.min() > 0.5 and noise.max() < 2.0
+
+
 @pytest.mark.parametrize("channels", [256, 4096, 65536])
 def test_cfg3_noise_and_percentile_sweep(abs_mode, channels):
     """Percentile5 / MAD sweep of BASELINE.json configs[2] on a slice of rows: bit-exact."""
