@@ -541,12 +541,21 @@ def chunked_form(template, queue, flagger, C: int, B: int, steps: int, timed, pe
         probe()
     queue.finish()
     ms_lanes = timed(probe, steps)
+    # stage by stage: one step at a time, the median over the steps of each stage's time (an
+    # event pair around every launch also catches whatever delays the host adds in between;
+    # the median keeps such a step from colouring the figure)
     _capi.profile_enable(True)
-    for _ in range(steps):
+    per_step = []
+    for _ in range(max(steps, 7)):
         probe()
-    queue.finish()
-    stages = _capi.profile_read()
+        queue.finish()
+        per_step.append(_capi.profile_read())
     _capi.profile_enable(False)
+    steps = 1
+    stages = {}
+    for name in per_step[0]:
+        times = sorted(rec[name][0] for rec in per_step)
+        stages[name] = (times[len(times) // 2], per_step[0][name][1])
     per_unit = {"background": 12.0, "noise": 4.0, "threshold": 4.125, "expand_flags": 1.125}
     names = {"background": "bg13_kernel", "noise": "madnz_stream_kernel",
              "threshold": "threshold_sum_kernel (two passes)", "expand_flags": "expand_flags_kernel"}
