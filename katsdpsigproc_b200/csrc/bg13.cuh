@@ -91,12 +91,12 @@ struct TileGeom {
     static constexpr int SMEM_BYTES = TILE_B * P * 4;
 };
 
-// Phase-1 work of one thread: U groups of 4 consecutive channels (the groups are 32 channels
+// Phase-1 work of one thread: U groups of 4 consecutive channels (the groups are GS channels
 // apart) of one baseline -> amplitudes (NaN where unusable) -> one 128-bit shared store per
 // group.  `p` addresses the sample (channel c, this thread's baseline), `fp` its flag;
 // row_bytes / flag_row are the distances to the next channel.  INTERIOR tiles skip every
 // bounds test.  Returns true if some sample is unusable.
-template <int IN_MODE, int FLAG_MODE, bool INTERIOR, int U>
+template <int IN_MODE, int FLAG_MODE, bool INTERIOR, int U, int GS = 32>
 __device__ __forceinline__ bool amplitudes_to_smem(const char *p, int64_t row_bytes,
                                                    const uint8_t *fp, int64_t flag_row, int c,
                                                    int C, float *dst)
@@ -108,10 +108,10 @@ __device__ __forceinline__ bool amplitudes_to_smem(const char *p, int64_t row_by
     // all loads first (predicated at most, no control flow in between), then the arithmetic
 #pragma unroll
     for (int u = 0; u < U; u++) {
-        const char *q = p + (int64_t) (32 * u) * row_bytes;
+        const char *q = p + (int64_t) (GS * u) * row_bytes;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-            const int ck = c + 32 * u + k;
+            const int ck = c + GS * u + k;
             const bool in = INTERIOR || (ck >= 0 && ck < C);
             raw[u][k] = make_float2(1.0f, 0.0f);
             if (IN_MODE == IN_AMP) {
@@ -126,7 +126,7 @@ __device__ __forceinline__ bool amplitudes_to_smem(const char *p, int64_t row_by
     if (FLAG_MODE != KSP_FLAGS_NONE) {
 #pragma unroll
         for (int u = 0; u < U; u++) {
-            const uint8_t *fq = fp + (int64_t) (32 * u) * flag_row;
+            const uint8_t *fq = fp + (int64_t) (GS * u) * flag_row;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
                 if ((usable >> (4 * u + k)) & 1u) {
@@ -175,22 +175,21 @@ __device__ __forceinline__ bool amplitudes_to_smem(const char *p, int64_t row_by
         }
         const float probe = (v[u][0] + v[u][1]) + (v[u][2] + v[u][3]);
         any_bad |= (probe != probe);                     // NaN iff some NaN (or inf - inf)
-        *reinterpret_cast<float4 *>(dst + 32 * u) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+        *reinterpret_cast<float4 *>(dst + GS * u) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
     }
     return any_bad;
 }
 
-template <int IN_MODE, int FLAG_MODE, bool INTERIOR, int TC>
-__device__ __forceinline__ bool tile_phase1(const BgArgs &a, int64_t b0, int c0, float *amp_sm)
+// NW warps (numbered `warp`) share the tile's groups: warp w takes groups w, w + NW, ...
+template <int IN_MODE, int FLAG_MODE, bool INTERIOR, int TC, int NW = BG_THREADS / 32>
+__device__ __forceinline__ bool tile_phase1(const BgArgs &a, int64_t b0, int c0, float *amp_sm,
+                                            const int warp, const int lane)
 {
     using G = TileGeom<TC>;
-    constexpr int NWARPS = BG_THREADS / 32;
-    static_assert(NWARPS == 8, "group schedule below assumes 8 warps");
+    constexpr int GS = 4 * NW;                           // channels covered by one group per warp
     constexpr int NEEDED = (TC + HALO_L + 6 + 3) / 4;    // groups that phase 2 reads
-    constexpr int FULL_ITERS = NEEDED / 16;              // 16 groups per block iteration (U = 2)
-    constexpr int REST = NEEDED - 16 * FULL_ITERS;       // < 16, handled with U = 1
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
+    constexpr int FULL_ITERS = NEEDED / (2 * NW);        // 2 NW groups per iteration (U = 2)
+    constexpr int REST = NEEDED - 2 * NW * FULL_ITERS;   // < 2 NW, handled with U = 1
     const int C = (int) a.channels;
     const int64_t b = min(b0 + lane, a.baselines - 1);   // clamp: duplicates are never stored
     constexpr int ESZ = (IN_MODE == IN_AMP) ? 4 : 8;
@@ -205,24 +204,24 @@ __device__ __forceinline__ bool tile_phase1(const BgArgs &a, int64_t b0, int c0,
     bool any_bad = false;
 #pragma unroll 1
     for (int i = 0; i < FULL_ITERS; i++) {
-        any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 2>(p, row_bytes, fp, flag_row,
-                                                                       c, C, dst);
-        p += 64 * row_bytes;
-        fp += 64 * flag_row;
-        c += 64;
-        dst += 64;
+        any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 2, GS>(p, row_bytes, fp, flag_row,
+                                                                           c, C, dst);
+        p += 2 * GS * row_bytes;
+        fp += 2 * GS * flag_row;
+        c += 2 * GS;
+        dst += 2 * GS;
     }
-    if (REST > 8) {
-        if (warp < REST - 8)
-            any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 2>(p, row_bytes, fp,
-                                                                           flag_row, c, C, dst);
+    if (REST > NW) {
+        if (warp < REST - NW)
+            any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 2, GS>(p, row_bytes, fp,
+                                                                               flag_row, c, C, dst);
         else
-            any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 1>(p, row_bytes, fp,
-                                                                           flag_row, c, C, dst);
+            any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 1, GS>(p, row_bytes, fp,
+                                                                               flag_row, c, C, dst);
     } else if (REST > 0) {
         if (warp < REST)
-            any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 1>(p, row_bytes, fp,
-                                                                           flag_row, c, C, dst);
+            any_bad |= amplitudes_to_smem<IN_MODE, FLAG_MODE, INTERIOR, 1, GS>(p, row_bytes, fp,
+                                                                               flag_row, c, C, dst);
     }
     return any_bad;
 }
@@ -237,15 +236,14 @@ __device__ __forceinline__ bool tile_phase1(const BgArgs &a, int64_t b0, int c0,
 #ifndef BG_X8
 #define BG_X8 1                      // phase 2 computes 8 medians per step (median13x8)
 #endif
-template <int IN_MODE, int TC, int PF>
-__device__ __forceinline__ bool tile_phase1_pipelined(const BgArgs &a, int64_t b0, int c0, float *amp_sm)
+template <int IN_MODE, int TC, int PF, int NW = BG_THREADS / 32>
+__device__ __forceinline__ bool tile_phase1_pipelined(const BgArgs &a, int64_t b0, int c0, float *amp_sm,
+                                                      const int warp, const int lane)
 {
     using G = TileGeom<TC>;
-    constexpr int NWARPS = BG_THREADS / 32;
+    constexpr int NWARPS = NW;
     constexpr int NEEDED = (TC + HALO_L + 6 + 3) / 4;    // groups that phase 2 reads
     constexpr int MAX_IT = (NEEDED + NWARPS - 1) / NWARPS;
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
     const int64_t b = min(b0 + lane, a.baselines - 1);
     const uint32_t row_bytes = (uint32_t) a.vis_stride * 8u;         // (the caller checks that it fits)
     const int n_it = (NEEDED - warp + NWARPS - 1) / NWARPS;          // groups warp, warp + 8, ...
@@ -311,29 +309,31 @@ struct BlockTile {               // grid (strips, channel tiles)
     static constexpr bool KEEP_IN_L2 = false;
 };
 
-template <int IN_MODE, int FLAG_MODE, bool TRANSPOSED, int TC, typename Where, int PF = BG_PF>
-__device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, float *amp_sm)
+// Phase 1 of a tile by NW warps (this thread: warp `warp`, lane `lane`): amplitudes into amp_sm.
+// Returns true if this thread stored an unusable sample (the tile then needs the checked phase 2).
+template <int IN_MODE, int FLAG_MODE, int TC, typename Where, int PF, int NW>
+__device__ __forceinline__ bool bg13_phase1(const BgArgs &a, const Where &at, float *amp_sm,
+                                            const int warp, const int lane)
+{
+    const int C = (int) a.channels;
+    const int64_t b0 = at.b0();
+    const int c0 = at.template c0<TC>();
+    const bool interior = (c0 - HALO_L >= 0) && (c0 + TC + HALO_R <= C);   // block-uniform
+    if (interior && IN_MODE == IN_NUMPY && FLAG_MODE == KSP_FLAGS_NONE && PF > 0 &&
+        a.vis_stride < ((int64_t) 1 << 28))
+        return tile_phase1_pipelined<IN_MODE, TC, PF, NW>(a, b0, c0, amp_sm, warp, lane);
+    if (interior)
+        return tile_phase1<IN_MODE, FLAG_MODE, true, TC, NW>(a, b0, c0, amp_sm, warp, lane);
+    return tile_phase1<IN_MODE, FLAG_MODE, false, TC, NW>(a, b0, c0, amp_sm, warp, lane);
+}
+
+// Phase 2 of a tile by BG_THREADS threads (this one: `tid`): medians, deviations, stores.
+template <int IN_MODE, int FLAG_MODE, bool TRANSPOSED, int TC, typename Where>
+__device__ __forceinline__ void bg13_phase2(const BgArgs &a, const Where &at, const float *amp_sm,
+                                            const int tile_bad, const int tid)
 {
     using G = TileGeom<TC>;
     const int C = (int) a.channels;
-    int tile_bad;
-
-    // ---- phase 1
-    {
-        const int64_t b0 = at.b0();
-        const int c0 = at.template c0<TC>();
-        const bool interior = (c0 - HALO_L >= 0) && (c0 + TC + HALO_R <= C);   // block-uniform
-        bool any_bad;
-        if (interior && IN_MODE == IN_NUMPY && FLAG_MODE == KSP_FLAGS_NONE && PF > 0 &&
-            a.vis_stride < ((int64_t) 1 << 28))
-            any_bad = tile_phase1_pipelined<IN_MODE, TC, PF>(a, b0, c0, amp_sm);
-        else if (interior)
-            any_bad = tile_phase1<IN_MODE, FLAG_MODE, true, TC>(a, b0, c0, amp_sm);
-        else
-            any_bad = tile_phase1<IN_MODE, FLAG_MODE, false, TC>(a, b0, c0, amp_sm);
-        // block-wide: does the tile need the checked path?
-        tile_bad = __syncthreads_or(any_bad);
-    }
     const int64_t b0 = at.b0();
     const int c0 = at.template c0<TC>();
     const int64_t row_off = at.row_off();
@@ -352,7 +352,7 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
             // computed once and each further run costs two additions (this part of the kernel is
             // bound by the ALU pipe, which the selection network needs for itself).
             constexpr int STEP_B = BG_THREADS / RUNS8;            // baseline rows between two runs of a thread
-            const int t = threadIdx.x;
+            const int t = tid;
             const int bl = 2 * (t / (2 * RUNS8)) + (t & 1);       // (see the general loop below)
             const int j = (t % (2 * RUNS8)) >> 1;
             const float *src = amp_sm + bl * G::P + 8 * j;
@@ -384,7 +384,7 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
             }
             return;
         }
-        for (int t = threadIdx.x; t < TILE_B * RUNS8; t += BG_THREADS) {
+        for (int t = tid; t < TILE_B * RUNS8; t += BG_THREADS) {
             int bl, j;
             if (TRANSPOSED) {
                 // lanes walk along channels, alternating between two baseline rows: 8 consecutive
@@ -441,7 +441,7 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
     // ---- phase 2, fast: no unusable sample anywhere in the tile
     if (!tile_bad) {
         constexpr int RUNS = TC / 4;                 // runs of 4 outputs per baseline row
-        for (int t = threadIdx.x; t < TILE_B * RUNS; t += BG_THREADS) {
+        for (int t = tid; t < TILE_B * RUNS; t += BG_THREADS) {
             int bl, j;
             if (TRANSPOSED) { bl = t / RUNS; j = t % RUNS; }      // lanes walk along channels
             else            { j = t / TILE_B; bl = t % TILE_B; }  // lanes walk along baselines
@@ -485,7 +485,7 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
     // ---- phase 2, checked: per-thread test of the 16 window samples
     {
         constexpr int RUNS = TC / 4;
-        for (int t = threadIdx.x; t < TILE_B * RUNS; t += BG_THREADS) {
+        for (int t = tid; t < TILE_B * RUNS; t += BG_THREADS) {
             int bl, j;
             if (TRANSPOSED) { bl = t / RUNS; j = t % RUNS; }
             else            { j = t / TILE_B; bl = t % TILE_B; }
@@ -524,6 +524,16 @@ __device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, floa
             }
         }
     }
+}
+
+// One tile by one block of BG_THREADS threads: phase 1, a block-wide vote, phase 2.
+template <int IN_MODE, int FLAG_MODE, bool TRANSPOSED, int TC, typename Where, int PF = BG_PF>
+__device__ __forceinline__ void bg13_tile(const BgArgs &a, const Where &at, float *amp_sm)
+{
+    const bool any_bad = bg13_phase1<IN_MODE, FLAG_MODE, TC, Where, PF, BG_THREADS / 32>(
+        a, at, amp_sm, (int) (threadIdx.x >> 5), (int) (threadIdx.x & 31));
+    const int tile_bad = __syncthreads_or(any_bad);       // does the tile need the checked path?
+    bg13_phase2<IN_MODE, FLAG_MODE, TRANSPOSED, TC, Where>(a, at, amp_sm, tile_bad, (int) threadIdx.x);
 }
 
 }  // namespace
