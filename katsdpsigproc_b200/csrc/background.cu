@@ -32,14 +32,17 @@ bg13_kernel(const BgArgs a)
 // phase 2 behind them; full / empty hand-over through named barriers (bar.arrive / bar.sync).
 // Both kinds of warp are always there, so the ALU pipe is fed while loads are in flight.
 // Baseline-major output only (the fused flagger's and ksp_background_median_filter_t's case).
-constexpr int WS_LOAD_WARPS = 4;
+#ifndef WS_LOAD_WARPS_N
+#define WS_LOAD_WARPS_N 8
+#endif
+constexpr int WS_LOAD_WARPS = WS_LOAD_WARPS_N;
 constexpr int WS_THREADS = 32 * WS_LOAD_WARPS + BG_THREADS;
 #ifndef WS_BUFS_N
 #define WS_BUFS_N 3
 #endif
 constexpr int WS_BUFS = WS_BUFS_N;
 #ifndef WS_PF
-#define WS_PF 3
+#define WS_PF 2
 #endif
 
 struct QueueTile {               // tile number -> coordinates, strips fastest
