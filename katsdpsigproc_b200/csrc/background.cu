@@ -11,7 +11,6 @@
 #include "common.cuh"
 #include "median13.cuh"
 #include "bg13.cuh"
-#include <stdlib.h>
 
 namespace {
 
@@ -21,124 +20,6 @@ bg13_kernel(const BgArgs a)
 {
     extern __shared__ __align__(16) float amp_sm[];     // [TILE_B][P]
     bg13_tile<IN_MODE, FLAG_MODE, TRANSPOSED, TC>(a, BlockTile(), amp_sm);
-}
-
-// ---------------------------------------------------------------- width 13, warp-specialised
-// The tile kernel above alternates between two very different phases - phase 1 waits for device
-// memory and works the FMA / XU pipes (amplitudes), phase 2 saturates the ALU pipe (min / max of
-// the selection network) - and only the chance overlap of the four blocks of an SM lets one
-// hide the other.  Here the two phases are different WARPS of a persistent block: 4 loader warps
-// run phase 1 of tile after tile into a ring of WS_BUFS shared-memory tiles, 8 median warps run
-// phase 2 behind them; full / empty hand-over through named barriers (bar.arrive / bar.sync).
-// Both kinds of warp are always there, so the ALU pipe is fed while loads are in flight.
-// Baseline-major output only (the fused flagger's and ksp_background_median_filter_t's case).
-#ifndef WS_LOAD_WARPS_N
-#define WS_LOAD_WARPS_N 8
-#endif
-constexpr int WS_LOAD_WARPS = WS_LOAD_WARPS_N;
-constexpr int WS_THREADS = 32 * WS_LOAD_WARPS + BG_THREADS;
-#ifndef WS_BUFS_N
-#define WS_BUFS_N 3
-#endif
-constexpr int WS_BUFS = WS_BUFS_N;
-#ifndef WS_PF
-#define WS_PF 2
-#endif
-
-struct QueueTile {               // tile number -> coordinates, strips fastest
-    int strip, ctile;
-    template <int TC> __device__ __forceinline__ int c0() const { return ctile * TC; }
-    __device__ __forceinline__ int64_t b0() const { return (int64_t) strip * 32; }
-    __device__ __forceinline__ int64_t row_off() const { return 0; }
-    static constexpr bool KEEP_IN_L2 = false;
-};
-
-// (barrier numbers as immediates: with a register operand ptxas reserves all 16 barriers)
-#define KSP_BAR_CASE(OP, N) case N: asm volatile(OP " " #N ", %0;" ::"n"(WS_THREADS) : "memory"); break;
-__device__ __forceinline__ void named_bar_sync(int id)
-{
-    switch (id) {
-    KSP_BAR_CASE("bar.sync", 1) KSP_BAR_CASE("bar.sync", 2) KSP_BAR_CASE("bar.sync", 3)
-    KSP_BAR_CASE("bar.sync", 4) KSP_BAR_CASE("bar.sync", 5) KSP_BAR_CASE("bar.sync", 6)
-    KSP_BAR_CASE("bar.sync", 7) KSP_BAR_CASE("bar.sync", 8)
-    }
-}
-__device__ __forceinline__ void named_bar_arrive(int id)
-{
-    switch (id) {
-    KSP_BAR_CASE("bar.arrive", 1) KSP_BAR_CASE("bar.arrive", 2) KSP_BAR_CASE("bar.arrive", 3)
-    KSP_BAR_CASE("bar.arrive", 4) KSP_BAR_CASE("bar.arrive", 5) KSP_BAR_CASE("bar.arrive", 6)
-    KSP_BAR_CASE("bar.arrive", 7) KSP_BAR_CASE("bar.arrive", 8)
-    }
-}
-#undef KSP_BAR_CASE
-static_assert(2 * WS_BUFS <= 8, "barrier numbers 1 .. 2 WS_BUFS");
-
-template <int IN_MODE, int FLAG_MODE, int TC>
-__global__ void __launch_bounds__(WS_THREADS, 2)
-bg13ws_kernel(const BgArgs a, const int n_strips, const int n_tiles)
-{
-    using G = TileGeom<TC>;
-    extern __shared__ __align__(16) float ws_sm[];            // WS_BUFS tiles
-    __shared__ int bad[WS_BUFS];                              // last use of the buffer that held an unusable sample
-    const int tid = threadIdx.x;
-    if (tid < WS_BUFS) bad[tid] = 0;
-    __syncthreads();
-    // barrier ids: 1 + buf "full" (loaders arrive, medians wait), 1 + WS_BUFS + buf "empty"
-    if (tid < 32 * WS_LOAD_WARPS) {
-        int k = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
-            const int buf = k % WS_BUFS;
-            if (k >= WS_BUFS) named_bar_sync(1 + WS_BUFS + buf);   // the medians are done with it
-            QueueTile at;
-            at.strip = tile % n_strips;
-            at.ctile = tile / n_strips;
-            const bool any_bad = bg13_phase1<IN_MODE, FLAG_MODE, TC, QueueTile, WS_PF, WS_LOAD_WARPS>(
-                a, at, ws_sm + buf * (G::SMEM_BYTES / 4), tid >> 5, tid & 31);
-            if (__any_sync(0xffffffffu, any_bad) && (tid & 31) == 0) atomicMax(&bad[buf], k + 1);
-            __threadfence_block();
-            named_bar_arrive(1 + buf);
-        }
-        // take the medians' last releases, so that no barrier is left half way
-        for (int j = max(k - WS_BUFS, 0); j < k; j++) named_bar_sync(1 + WS_BUFS + j % WS_BUFS);
-    } else {
-        const int mt = tid - 32 * WS_LOAD_WARPS;
-        int k = 0;
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, k++) {
-            const int buf = k % WS_BUFS;
-            named_bar_sync(1 + buf);
-            QueueTile at;
-            at.strip = tile % n_strips;
-            at.ctile = tile / n_strips;
-            const int tile_bad = *reinterpret_cast<volatile int *>(&bad[buf]) == k + 1;
-            bg13_phase2<IN_MODE, FLAG_MODE, true, TC, QueueTile>(a, at, ws_sm + buf * (G::SMEM_BYTES / 4),
-                                                                 tile_bad, mt);
-            __threadfence_block();
-            named_bar_arrive(1 + WS_BUFS + buf);
-        }
-    }
-}
-
-template <int IN_MODE, int FLAG_MODE>
-int launch_bg13ws(cudaStream_t s, const BgArgs &a)
-{
-    auto kernel = bg13ws_kernel<IN_MODE, FLAG_MODE, BG_TC>;
-    constexpr int smem = WS_BUFS * TileGeom<BG_TC>::SMEM_BYTES;
-    static bool configured[64];
-    int dev = 0;
-    KSP_CUDA(cudaGetDevice(&dev));
-    if (dev >= 0 && dev < 64 && !configured[dev]) {
-        KSP_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured[dev] = true;
-    }
-    const int64_t n_strips = ksp_divup(a.baselines, TILE_B), n_ctiles = ksp_divup(a.channels, BG_TC);
-    if (n_strips * n_ctiles > 0x7fffffff) return KSP_ETOOLARGE;
-    const int n_tiles = (int) (n_strips * n_ctiles);
-    int blocks = 2 * ksp_sm_count();
-    if (blocks > n_tiles) blocks = n_tiles;
-    kernel<<<blocks, WS_THREADS, smem, s>>>(a, (int) n_strips, n_tiles);
-    KSP_CHECK_LAUNCH();
-    return 0;
 }
 
 // ---------------------------------------------------------------- any odd width
@@ -425,14 +306,8 @@ int launch_bg(cudaStream_t s, const void *vis, float *out, const uint8_t *flags,
         KSP_CHECK_LAUNCH();
         return 0;
     }
-    // baseline-major output: the warp-specialised persistent kernel (KSP_BG_WS=0: the tile kernel)
-    static const bool use_ws = [] {
-        const char *e = getenv("KSP_BG_WS");
-        return !(e && atoi(e) == 0);
-    }();
 #define KSP_BG_CASE(IM, FM)                                                        \
     if (in_mode == IM && flag_mode == FM) {                                        \
-        if (TRANSPOSED && use_ws) return launch_bg13ws<IM, FM>(s, a);              \
         if (TileGeom<BG_TC>::SMEM_BYTES > 48 * 1024)                               \
             KSP_CUDA(cudaFuncSetAttribute(bg13_kernel<IM, FM, TRANSPOSED, BG_TC>,  \
                                           cudaFuncAttributeMaxDynamicSharedMemorySize, \
