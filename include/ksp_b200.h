@@ -222,6 +222,41 @@ int ksp_flagger_stats(void *stream, const ksp_flagger_params *p, const void *scr
 int ksp_flagger_is_dataflow(const ksp_flagger_params *p);
 
 /* ------------------------------------------------------------------------
+ * 2-D flagger: SumThresholdFlagger of rfi/twodflag.py:894-1118 (numba, CPU only in the reference)
+ * for a (time, freq, baseline) block of visibilities or magnitudes, baseline fastest.  The
+ * caller conditions the parameters as the reference's Python does (twodflag.py:951-1026): window
+ * lists clipped and de-duplicated, rho ** log2(window) per window, box radii of the Gaussian
+ * approximations per background iteration, frequency-chunk boundaries in averaged channels.
+ * Flags are identical to the reference's (the float64 running sums keep its order).
+ * ---------------------------------------------------------------------- */
+#define KSP_TWOD_MAX_WINDOWS 16      /* window sizes per axis */
+#define KSP_TWOD_MAX_WINDOW 64       /* largest window size */
+#define KSP_TWOD_MAX_CHUNKS 64       /* frequency chunks */
+#define KSP_TWOD_MAX_ITERATIONS 63   /* background iterations */
+typedef struct ksp_twodflag_params {
+    int64_t n_time, n_freq, n_bl;    /* shape of data / in_flags / out_flags, C order */
+    int is_complex;                  /* data is complex64 (else float32 magnitudes) */
+    int average_freq;                /* channels averaged before flagging */
+    int n_windows_time, n_windows_freq;
+    int windows_time[KSP_TWOD_MAX_WINDOWS], windows_freq[KSP_TWOD_MAX_WINDOWS];
+    double tf_time[KSP_TWOD_MAX_WINDOWS], tf_freq[KSP_TWOD_MAX_WINDOWS];   /* pow(rho, log2(window)) */
+    double outlier_nsigma, background_reject;
+    int background_iterations;
+    int r_time[KSP_TWOD_MAX_ITERATIONS + 1];   /* box radius for extend factor e = 1 .. iterations */
+    int r_freq[KSP_TWOD_MAX_ITERATIONS + 1];   /* (index 0 unused): int(0.5 sqrt(12 (e sigma)^2 / 4 + 1)) */
+    int time_extend, freq_extend;
+    int n_chunks;
+    int64_t chunk_ends[KSP_TWOD_MAX_CHUNKS + 1];   /* 0 = chunk_ends[0] <= ... <= chunk_ends[n_chunks] = averaged channels */
+    double flag_all_time_frac, flag_all_freq_frac;
+} ksp_twodflag_params;
+
+/* Scratch for `batch_baselines` baselines in flight (0: bad parameters). */
+size_t ksp_twodflag_scratch_bytes(const ksp_twodflag_params *p, int64_t batch_baselines);
+/* data: complex64 or float32; in_flags: uint8, non-zero = ignore; out_flags: uint8 0 / 1. */
+int ksp_twodflag(void *stream, const ksp_twodflag_params *p, const void *data, const uint8_t *in_flags,
+                 uint8_t *out_flags, void *scratch, size_t scratch_bytes, int64_t batch_baselines);
+
+/* ------------------------------------------------------------------------
  * General-purpose operations that sit beside the RFI ones in the reference.
  * ---------------------------------------------------------------------- */
 /* Fill.  Replaces fill.mako (reference fill.py:130-139): data[i] = *value for

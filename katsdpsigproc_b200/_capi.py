@@ -53,6 +53,31 @@ class FlaggerParams(ctypes.Structure):
     ]
 
 
+TWOD_MAX_WINDOWS = 16
+TWOD_MAX_WINDOW = 64
+TWOD_MAX_CHUNKS = 64
+TWOD_MAX_ITERATIONS = 63
+
+
+class TwodflagParams(ctypes.Structure):
+    """Mirror of ``ksp_twodflag_params``."""
+
+    _fields_ = [
+        ("n_time", c_int64), ("n_freq", c_int64), ("n_bl", c_int64),
+        ("is_complex", c_int), ("average_freq", c_int),
+        ("n_windows_time", c_int), ("n_windows_freq", c_int),
+        ("windows_time", c_int * TWOD_MAX_WINDOWS), ("windows_freq", c_int * TWOD_MAX_WINDOWS),
+        ("tf_time", c_double * TWOD_MAX_WINDOWS), ("tf_freq", c_double * TWOD_MAX_WINDOWS),
+        ("outlier_nsigma", c_double), ("background_reject", c_double),
+        ("background_iterations", c_int),
+        ("r_time", c_int * (TWOD_MAX_ITERATIONS + 1)), ("r_freq", c_int * (TWOD_MAX_ITERATIONS + 1)),
+        ("time_extend", c_int), ("freq_extend", c_int),
+        ("n_chunks", c_int),
+        ("chunk_ends", c_int64 * (TWOD_MAX_CHUNKS + 1)),
+        ("flag_all_time_frac", c_double), ("flag_all_freq_frac", c_double),
+    ]
+
+
 # name -> (restype, argtypes); every symbol declared in include/ksp_b200.h
 PROTOTYPES = {
     "ksp_abi_version": (c_int, []),
@@ -140,6 +165,11 @@ PROTOTYPES = {
     "ksp_flagger_stats": (
         c_int, [c_void_p, POINTER(FlaggerParams), c_void_p, POINTER(ctypes.c_ulonglong), c_int]),
     "ksp_flagger_is_dataflow": (c_int, [POINTER(FlaggerParams)]),
+    "ksp_twodflag_scratch_bytes": (c_size_t, [POINTER(TwodflagParams), c_int64]),
+    "ksp_twodflag": (
+        c_int,
+        [c_void_p, POINTER(TwodflagParams), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64],
+    ),
 }
 
 _lib: Optional[ctypes.CDLL] = None

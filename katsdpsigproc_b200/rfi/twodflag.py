@@ -1,0 +1,166 @@
+"""2-D RFI flagger: ``SumThresholdFlagger`` of the reference (``rfi/twodflag.py:894-1118``) on the GPU.
+
+Same constructor, same ``get_flags(data, flags)`` with ``(time, frequency, baseline)`` arrays, same
+flags - the reference's is a numba CPU implementation whose float64 running sums fix the result
+to the last bit; ``csrc/twodflag.cu`` keeps those recurrences in the reference's order and takes
+its parallelism from the baselines (and, inside a baseline, from the rows / columns that the
+reference loops over independently).  Parameter conditioning (window clipping, frequency-chunk
+boundaries, box radii of the Gaussian approximations, ``rho ** log2(window)``) is done here in
+Python with the same expressions as the reference's ``__init__`` / ``_get_flags``
+(``twodflag.py:951-1026,341,527``) and handed to the C ABI as plain numbers.
+
+There is no CPU implementation in this module: without the CUDA library it fails on import of
+the library, not silently.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref, c_size_t
+from typing import Any, Optional, Sequence
+
+import numpy as np
+
+from .. import _capi, accel
+
+
+def _as_min_dtype(value: int) -> np.generic:
+    """The smallest unsigned integer type that holds ``value`` (reference ``twodflag.py:28-42``;
+    kept because ``time_extend`` / ``freq_extend`` / ``average_freq`` are public attributes)."""
+    if value >= 0:
+        for dtype in (np.uint8, np.uint16, np.uint32, np.uint64):
+            if value <= np.iinfo(dtype).max:
+                return dtype(value)
+    raise ValueError("Value must be a non-negative integer that fits in 64 bits")
+
+
+class SumThresholdFlagger:
+    """Flagger that detects spikes along both the frequency and the time axis (SumThreshold,
+    Offringa 2010).  Parameters as the reference's class of the same name
+    (``twodflag.py:917-949``); ``context`` (extension, keyword only) is the device context to run
+    on - by default one is created on first use with :func:`accel.create_some_context`.
+    """
+
+    def __init__(self, outlier_nsigma: float = 4.5, windows_time: Sequence[int] = (1, 2, 4, 8),
+                 windows_freq: Sequence[int] = (1, 2, 4, 8), background_reject: float = 2.0,
+                 background_iterations: int = 1, spike_width_time: float = 12.5,
+                 spike_width_freq: float = 10.0, time_extend: int = 3, freq_extend: int = 3,
+                 freq_chunks: int = 10, average_freq: int = 1, flag_all_time_frac: float = 0.6,
+                 flag_all_freq_frac: float = 0.8, rho: float = 1.3, *, context: Any = None) -> None:
+        self.outlier_nsigma = outlier_nsigma
+        self.windows_time = windows_time
+        # scale the frequency windows by the averaging, drop duplicates (twodflag.py:969-971)
+        scaled = np.ceil(np.array(windows_freq, dtype=np.float32) / average_freq)
+        self.windows_freq = np.unique(scaled.astype(np.int_))
+        self.background_reject = background_reject
+        self.background_iterations = background_iterations
+        self.spike_width_time = spike_width_time
+        self.spike_width_freq = spike_width_freq / average_freq
+        self.time_extend = _as_min_dtype(time_extend)
+        self.freq_extend = _as_min_dtype(freq_extend)
+        self.freq_chunks = freq_chunks
+        self.average_freq = _as_min_dtype(average_freq)
+        self.flag_all_time_frac = flag_all_time_frac
+        self.flag_all_freq_frac = flag_all_freq_frac
+        self.rho = rho
+        self._context = context
+        self._queue: Any = None
+
+    # ------------------------------------------------------------------ parameters for the C ABI
+    def _params(self, shape: Sequence[int], is_complex: bool) -> "_capi.TwodflagParams":
+        n_time, n_freq, n_bl = (int(x) for x in shape)
+        average_freq = int(self.average_freq)
+        averaged = (n_freq + average_freq - 1) // average_freq
+        chunk_ends = np.linspace(0, averaged, self.freq_chunks + 1).astype(np.int_)
+        # clipped to the data (the time windows against shape[1], as the reference does)
+        windows_time = [int(w) for w in self.windows_time if w <= n_freq]
+        windows_freq = [int(w) for w in self.windows_freq if w <= averaged]
+        p = _capi.TwodflagParams()
+        p.n_time, p.n_freq, p.n_bl = n_time, n_freq, n_bl
+        p.is_complex = int(is_complex)
+        p.average_freq = average_freq
+        for name, windows in (("time", windows_time), ("freq", windows_freq)):
+            if len(windows) > _capi.TWOD_MAX_WINDOWS:
+                raise ValueError(f"at most {_capi.TWOD_MAX_WINDOWS} window sizes per axis")
+            if windows and max(windows) > _capi.TWOD_MAX_WINDOW:
+                raise ValueError(f"window sizes up to {_capi.TWOD_MAX_WINDOW} are supported")
+            setattr(p, f"n_windows_{name}", len(windows))
+            for i, w in enumerate(windows):
+                getattr(p, f"windows_{name}")[i] = w
+                getattr(p, f"tf_{name}")[i] = pow(self.rho, np.log2(w))       # twodflag.py:527
+        p.outlier_nsigma = self.outlier_nsigma
+        p.background_reject = self.background_reject
+        if not 1 <= self.background_iterations <= _capi.TWOD_MAX_ITERATIONS:
+            raise ValueError(f"background_iterations must be 1 .. {_capi.TWOD_MAX_ITERATIONS}")
+        p.background_iterations = self.background_iterations
+        passes = 4
+        for extend_factor in range(1, self.background_iterations + 1):
+            sigma = extend_factor * np.array((self.spike_width_time, self.spike_width_freq))
+            r = (0.5 * np.sqrt(12.0 * sigma**2 / passes + 1)).astype(np.int_)   # twodflag.py:341
+            p.r_time[extend_factor] = int(r[0])
+            p.r_freq[extend_factor] = int(r[1])
+        p.time_extend = int(self.time_extend)
+        p.freq_extend = int(self.freq_extend)
+        if not 1 <= self.freq_chunks <= _capi.TWOD_MAX_CHUNKS:
+            raise ValueError(f"freq_chunks must be 1 .. {_capi.TWOD_MAX_CHUNKS}")
+        p.n_chunks = self.freq_chunks
+        for i, end in enumerate(chunk_ends):
+            p.chunk_ends[i] = int(end)
+        p.flag_all_time_frac = self.flag_all_time_frac
+        p.flag_all_freq_frac = self.flag_all_freq_frac
+        return p
+
+    def _ensure_queue(self) -> Any:
+        if self._queue is None:
+            if self._context is None:
+                self._context = accel.create_some_context(interactive=False)
+            self._queue = self._context.create_command_queue()
+        return self._queue
+
+    # ------------------------------------------------------------------ the reference's entry point
+    def get_flags(self, data: np.ndarray, flags: np.ndarray, pool: Any = None,
+                  chunk_size: Optional[int] = None, is_multiprocess: Optional[bool] = None
+                  ) -> np.ndarray:
+        """Flags for ``data`` (``(time, frequency, baseline)``, complex64 visibilities or real
+        magnitudes); ``flags`` of the same shape marks samples to ignore.  Returns a bool array of
+        that shape.  ``pool`` and ``is_multiprocess`` (the reference's CPU executors) are accepted
+        and ignored; ``chunk_size`` is the number of baselines in flight on the device at a time
+        (default: enough to fill it, within ~4 GB of scratch).
+        """
+        if data.shape != flags.shape:
+            raise ValueError("Shape mismatch")
+        if data.ndim != 3:
+            raise ValueError("data has wrong number of dimensions")
+        is_complex = np.iscomplexobj(data)
+        host_data = np.ascontiguousarray(data, np.complex64 if is_complex else np.float32)
+        host_flags = np.ascontiguousarray(flags).astype(np.uint8, copy=False)
+        if host_flags.dtype != np.uint8 or flags.dtype != np.bool_:
+            host_flags = (np.ascontiguousarray(flags) != 0).astype(np.uint8)
+        out = np.empty(data.shape, np.bool_)
+        if data.size == 0:
+            return out
+        p = self._params(data.shape, is_complex)
+        queue = self._ensure_queue()
+        context = queue.context
+        lib = _capi.load()
+        context._make_current()
+        per_baseline = int(lib.ksp_twodflag_scratch_bytes(byref(p), 1))
+        if per_baseline == 0:
+            raise ValueError("parameters outside the supported range")
+        n_bl = data.shape[2]
+        if not chunk_size:
+            chunk_size = max(1, min(n_bl, 4 * 148, (4 << 30) // per_baseline))
+        chunk_size = int(min(chunk_size, n_bl))
+        d_data = accel.DeviceArray(context, host_data.shape, host_data.dtype)
+        d_flags = accel.DeviceArray(context, host_flags.shape, np.uint8)
+        d_out = accel.DeviceArray(context, host_flags.shape, np.uint8)
+        d_scratch = accel.DeviceArray(context, (per_baseline * chunk_size,), np.uint8)
+        d_data.set(queue, host_data)
+        d_flags.set(queue, host_flags)
+        _capi.call("ksp_twodflag", ctypes.c_void_p(queue.stream), byref(p),
+                   ctypes.c_void_p(d_data.buffer.ptr), ctypes.c_void_p(d_flags.buffer.ptr),
+                   ctypes.c_void_p(d_out.buffer.ptr), ctypes.c_void_p(d_scratch.buffer.ptr),
+                   c_size_t(per_baseline * chunk_size), ctypes.c_int64(chunk_size))
+        result = d_out.get(queue)
+        np.not_equal(result, 0, out=out)
+        return out

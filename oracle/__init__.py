@@ -41,3 +41,14 @@ def reference_host() -> Optional[Any]:
         return importlib.import_module("katsdpsigproc.rfi.host")
     except Exception:
         return None
+
+
+def reference_twodflag() -> Optional[Any]:
+    """The reference's own ``katsdpsigproc.rfi.twodflag`` module (numba) from ``oracle/_ref``, or
+    ``None`` if it is not there or numba is missing."""
+    if reference_host() is None:
+        return None
+    try:
+        return importlib.import_module("katsdpsigproc.rfi.twodflag")
+    except Exception:
+        return None

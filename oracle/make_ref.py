@@ -3,7 +3,8 @@
 TEST INFRASTRUCTURE ONLY -- see ``oracle/__init__.py``.
 
 The reference's CPU path is pure Python (``src/katsdpsigproc/rfi/host.py`` and the constant in
-``rfi/__init__.py``; numpy + pandas only).  Where the reference checkout is present (the build
+``rfi/__init__.py``; numpy + pandas only); its 2-D flagger ``rfi/twodflag.py`` is Python compiled
+by numba (present in this image).  Where the reference checkout is present (the build
 container: ``/root/reference``), this script places those two files, unmodified, under
 ``oracle/_ref/katsdpsigproc/rfi/`` -- git-ignored build output that travels to the GPU box
 with the snapshot, like the compiled libraries -- so that ``bench.py``'s CPU legs can time the
@@ -23,7 +24,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 DEST = os.path.join(HERE, "_ref", "katsdpsigproc")
-FILES = ("rfi/__init__.py", "rfi/host.py")
+FILES = ("rfi/__init__.py", "rfi/host.py", "rfi/twodflag.py")
 
 
 def make(reference_root: str = "/root/reference") -> bool:
