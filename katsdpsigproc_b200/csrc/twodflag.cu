@@ -207,7 +207,25 @@ __device__ void box_line(const float *data, int64_t stride, float *padded, int64
         stop = min(stop, len);
         const int tail = min(stop, len - 2 * r);
         for (int i = prev_start; i < min(start + 2 * r, len); i++) s += (double) padded[(int64_t) i * pstride];
-        for (int i = start; i < tail; i++) {
+        // Step i reads padded[i + 2 r] and padded[i] and writes padded[i]: every read is of an
+        // element no earlier step wrote, so the loads of a batch of steps are issued together and
+        // only the two float64 additions per step stay serial.
+        int i = start;
+        for (; i + 8 <= tail; i += 8) {
+            float in[8], prev[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                in[k] = padded[(int64_t) (i + k + 2 * r) * pstride];
+                prev[k] = padded[(int64_t) (i + k) * pstride];
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                s += (double) in[k];
+                padded[(int64_t) (i + k) * pstride] = (float) s;
+                s -= (double) prev[k];
+            }
+        }
+        for (; i < tail; i++) {
             s += (double) padded[(int64_t) (i + 2 * r) * pstride];
             const float prev = padded[(int64_t) i * pstride];
             padded[(int64_t) i * pstride] = (float) s;
