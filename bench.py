@@ -436,6 +436,10 @@ def b200_arm(args) -> None:
         del stream
         cfg5 = cfg5_block(template, queue, context, rank, world, barrier, reduce_max, args)
 
+    twod = None
+    if rank == 0 and args.twodflag:
+        twod = twodflag_block(context)
+
     if rank == 0:
         total_vis = n_vis * world
         h2d = int(np.prod(vis_dev.padded_shape)) * vis_dev.dtype.itemsize
@@ -459,6 +463,7 @@ def b200_arm(args) -> None:
             "parity": parity,
             "roofline": roofline,
             "cfg5": cfg5,
+            "twodflag": twod,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
@@ -573,6 +578,80 @@ def chunked_form(template, queue, flagger, C: int, B: int, steps: int, timed, pe
     }
     del probe
     return out
+
+
+def twodflag_block(context) -> dict:
+    """`--twodflag`: the 2-D flagger (rfi.twodflag.SumThresholdFlagger) on a 16 x 4096 x 1024
+    complex64 block: device time, time through get_flags with host arrays, and the reference's numba
+    implementation (oracle/_ref) with a thread pool on the host cores on 64 of the baselines, flags
+    compared."""
+    import concurrent.futures
+    import ctypes
+    from ctypes import byref, c_size_t
+
+    import numpy as np
+
+    import oracle
+    from katsdpsigproc_b200 import _capi, accel
+    from katsdpsigproc_b200.rfi import twodflag
+
+    shape = (16, 4096, 1024)
+    rs = np.random.RandomState(1)
+    mag = (4.0 + np.sin(np.linspace(0, 6, shape[1]))[None, :, None]
+           + rs.standard_normal(shape).astype(np.float32) * 0.1).astype(np.float32)
+    mag[4:6, shape[1] // 3:shape[1] // 2, :] += 0.7
+    mag[:, shape[1] // 5, :] += 0.5
+    mag[rs.random_sample(shape) < 0.003] += 3.0
+    phase = rs.random_sample(shape).astype(np.float32) * np.float32(2 * np.pi)
+    vis = (mag * np.exp(1j * phase)).astype(np.complex64)
+    flags = rs.random_sample(shape) < 0.02
+    flagger = twodflag.SumThresholdFlagger(context=context)
+    flagger.get_flags(vis, flags)
+    t0 = time.perf_counter()
+    out = flagger.get_flags(vis, flags)
+    e2e = time.perf_counter() - t0
+    queue = context.create_command_queue()
+    p = flagger._params(shape, True)
+    lib = _capi.load()
+    per_bl = int(lib.ksp_twodflag_scratch_bytes(byref(p), 1))
+    batch = max(1, min(shape[2], 4 * 148, (4 << 30) // per_bl))
+    d_vis = accel.DeviceArray(context, vis.shape, vis.dtype)
+    d_fl = accel.DeviceArray(context, vis.shape, np.uint8)
+    d_out = accel.DeviceArray(context, vis.shape, np.uint8)
+    d_scr = accel.DeviceArray(context, (per_bl * batch,), np.uint8)
+    d_vis.set(queue, vis)
+    d_fl.set(queue, flags.astype(np.uint8))
+    times = []
+    for _ in range(4):
+        a = queue.enqueue_marker()
+        _capi.call("ksp_twodflag", ctypes.c_void_p(queue.stream), byref(p), ctypes.c_void_p(d_vis.buffer.ptr),
+                   ctypes.c_void_p(d_fl.buffer.ptr), ctypes.c_void_p(d_out.buffer.ptr),
+                   ctypes.c_void_p(d_scr.buffer.ptr), c_size_t(per_bl * batch), ctypes.c_int64(batch))
+        m = queue.enqueue_marker()
+        queue.finish()
+        times.append(m.time_since(a))
+    dev = sorted(times[1:])[1]
+    res = {"workload": "SumThresholdFlagger.get_flags, 16 dumps x 4096 channels x 1024 baselines complex64, default parameters",
+           "samples": vis.size, "flagged_fraction": float(out.mean()),
+           "device_s": dev, "device_samples_per_s": vis.size / dev,
+           "e2e_s": e2e, "e2e_samples_per_s": vis.size / e2e}
+    ref = oracle.reference_twodflag()
+    if ref is not None:
+        nb = 64
+        sub_v, sub_f = np.ascontiguousarray(vis[..., :nb]), np.ascontiguousarray(flags[..., :nb])
+        cpu = ref.SumThresholdFlagger()
+        cpu.get_flags(sub_v[..., :2], sub_f[..., :2])             # numba compilation
+        cores = host_cores()
+        with concurrent.futures.ThreadPoolExecutor(cores) as pool:
+            t0 = time.perf_counter()
+            want = cpu.get_flags(sub_v, sub_f, pool=pool)
+            cpu_s = time.perf_counter() - t0
+        res["cpu_reference"] = {"kind": "reference", "what": "katsdpsigproc.rfi.twodflag.SumThresholdFlagger (numba), "
+                                "unmodified (oracle/_ref), ThreadPoolExecutor", "threads": cores, "baselines": nb,
+                                "samples_per_s": sub_v.size / cpu_s}
+        res["flag_mismatches_vs_reference"] = int(np.count_nonzero(want != out[..., :nb]))
+        res["baselines_compared"] = nb
+    return res
 
 
 CFG5_BASELINES = 12960
@@ -701,6 +780,8 @@ def main() -> None:
     ap.add_argument("--no-stages", action="store_true",
                     help="skip the chunked form's per-stage timings")
     ap.add_argument("--no-cfg5", action="store_true", help="skip the configs[4] block")
+    ap.add_argument("--twodflag", action="store_true",
+                    help="also measure the 2-D flagger against the reference's numba implementation")
     ap.add_argument("--quick", action="store_true",
                     help="only the two timed legs: no CPU baseline, parity, stages or cfg5")
     args = ap.parse_args()

@@ -1,11 +1,9 @@
-"""Throughput of the 2-D flagger (developer tool, GPU only): katsdpsigproc_b200's CUDA
-SumThresholdFlagger against the reference's numba implementation (oracle/_ref) on the box's host
-cores, same input, flags compared.
+"""Throughput of the 2-D flagger on the device (developer tool, GPU only).  The comparison with
+the reference's numba implementation on the host cores is `python bench.py --twodflag`.
 
-    python tools/time_twodflag.py [n_time n_freq n_bl] [--cpu-baselines N] [--reps R]
+    python tools/time_twodflag.py [n_time n_freq n_bl] [--reps R]
 """
 import argparse
-import concurrent.futures
 import ctypes
 import json
 import os
@@ -16,7 +14,6 @@ from ctypes import byref, c_size_t
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import oracle  # noqa: E402
 from katsdpsigproc_b200 import _capi, accel  # noqa: E402
 from katsdpsigproc_b200.rfi import twodflag  # noqa: E402
 
@@ -37,7 +34,7 @@ def make_input(rs, shape):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("shape", type=int, nargs="*", default=[16, 4096, 1024])
-    ap.add_argument("--cpu-baselines", type=int, default=64)
+    ap.add_argument("--cpu-baselines", type=int, default=0, help="ignored (see bench.py --twodflag)")
     ap.add_argument("--reps", type=int, default=3)
     args = ap.parse_args()
     shape = tuple(args.shape)
@@ -78,20 +75,6 @@ def main():
            "gpu_device_s": dev, "gpu_device_Msamples_s": n / dev / 1e6,
            "gpu_end_to_end_s": e2e, "gpu_end_to_end_Msamples_s": n / e2e / 1e6, "first_call_s": first,
            "scratch_MB_per_baseline": per_bl / 1e6, "baselines_in_flight": batch}
-    ref = oracle.reference_twodflag()
-    if ref is not None and args.cpu_baselines > 0:
-        nb = min(args.cpu_baselines, shape[2])
-        sub_v, sub_f = np.ascontiguousarray(vis[..., :nb]), np.ascontiguousarray(flags[..., :nb])
-        cpu = ref.SumThresholdFlagger()
-        cpu.get_flags(sub_v[..., :2], sub_f[..., :2])             # numba compilation
-        cores = len(os.sched_getaffinity(0))
-        with concurrent.futures.ThreadPoolExecutor(cores) as pool:
-            t0 = time.perf_counter()
-            want = cpu.get_flags(sub_v, sub_f, pool=pool)
-            cpu_s = time.perf_counter() - t0
-        res.update({"cpu_reference_baselines": nb, "cpu_reference_threads": cores,
-                    "cpu_reference_s": cpu_s, "cpu_reference_Msamples_s": sub_v.size / cpu_s / 1e6,
-                    "flag_mismatches_vs_reference": int(np.count_nonzero(want != out[..., :nb]))})
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     with open(os.environ.get("TK_OUT", "gpurun_out/time_twodflag.json"), "w") as f:
