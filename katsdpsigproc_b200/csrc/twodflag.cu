@@ -46,6 +46,7 @@ struct TdArgs {
 // ---- per-baseline scratch layout (A = n_time * a_freq elements)
 struct TdBuffers {
     float *data, *bg, *weight, *pad, *vals;
+    int64_t pad_n;               // floats per work area of `pad` (there are two)
     float *spec_data, *spec_bg, *spec_weight;
     uint8_t *flags, *work, *tfl, *ffl, *pos, *neg, *hp, *hn, *spec_flags, *spec_work, *spec_out, *comb;
     uint8_t *outb;               // (n_time, n_freq) flags of this baseline at the original resolution
@@ -66,7 +67,7 @@ __host__ __device__ inline size_t td_layout(const ksp_twodflag_params &p, int a_
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += td_align(bytes); return base ? base + o : (char *) nullptr; };
     float *f_data = (float *) take(A * 4), *f_bg = (float *) take(A * 4), *f_w = (float *) take(A * 4);
-    float *f_pad = (float *) take(pad_n * 4), *f_vals = (float *) take(A * 4);
+    float *f_pad = (float *) take(2 * pad_n * 4), *f_vals = (float *) take(A * 4);
     float *s_data = (float *) take(F * 4), *s_bg = (float *) take(F * 4), *s_w = (float *) take(F * 4);
     const size_t W = T * td_row_work(p, a_freq, max_wf);       // >= A
     uint8_t *u[12];
@@ -79,6 +80,7 @@ __host__ __device__ inline size_t td_layout(const ksp_twodflag_params &p, int a_
     float *thr = (float *) take((T + 1) * (size_t) (p.n_chunks > 0 ? p.n_chunks : 1) * 4);
     if (b) {
         b->data = f_data; b->bg = f_bg; b->weight = f_w; b->pad = f_pad; b->vals = f_vals;
+        b->pad_n = (int64_t) pad_n;
         b->spec_data = s_data; b->spec_bg = s_bg; b->spec_weight = s_w;
         b->flags = u[0]; b->work = u[1]; b->tfl = u[2]; b->ffl = u[3]; b->pos = u[4]; b->neg = u[5];
         b->hp = u[6]; b->hn = u[7]; b->spec_flags = u[8]; b->spec_work = u[9]; b->spec_out = u[10];
@@ -251,27 +253,37 @@ __device__ __forceinline__ float box_divisor(int r)
     return __fmul_rn(d2, d2);
 }
 
-// In-place 2-D filter of arr (T x F): time axis (one thread per column), then frequency (per row).
-__device__ void box_filter_2d(float *arr, int T, int F, int r_t, int r_f, float *pad)
+// In-place 2-D filter of TWO arrays (T x F each; they are independent, so their lines run side
+// by side): time axis (one thread per array and column), then frequency (per array and row).
+// pad: two work areas of pad_n floats.
+__device__ void box_filter_2d_pair(float *arr0, float *arr1, int T, int F, int r_t, int r_f, float *pad,
+                                   int64_t pad_n)
 {
     const int tid = threadIdx.x;
     if (r_t > 0) {
         const float div = box_divisor(r_t);
-        for (int f = tid; f < F; f += TD_THREADS) box_line(arr + f, F, pad + f, F, T, r_t, arr + f, F, div);
+        for (int i = tid; i < 2 * F; i += TD_THREADS) {
+            const int which = i >= F, f = which ? i - F : i;
+            float *arr = which ? arr1 : arr0;
+            box_line(arr + f, F, pad + which * pad_n + f, F, T, r_t, arr + f, F, div);
+        }
         __syncthreads();
     }
     if (r_f > 0) {
         const float div = box_divisor(r_f);
         const int64_t plen = F + (int64_t) r_f * TD_PASSES;
-        for (int t = tid; t < T; t += TD_THREADS)
-            box_line(arr + (int64_t) t * F, 1, pad + t * plen, 1, F, r_f, arr + (int64_t) t * F, 1, div);
+        for (int i = tid; i < 2 * T; i += TD_THREADS) {
+            const int which = i >= T, t = which ? i - T : i;
+            float *arr = which ? arr1 : arr0;
+            box_line(arr + (int64_t) t * F, 1, pad + which * pad_n + t * plen, 1, F, r_f, arr + (int64_t) t * F, 1, div);
+        }
         __syncthreads();
     }
 }
 
 // twodflag.py:360-400
 __device__ void masked_gaussian(const float *data, const uint8_t *flags, int T, int F, int r_t, int r_f,
-                                float *out, float *weight, float *pad)
+                                float *out, float *weight, float *pad, int64_t pad_n)
 {
     const int tid = threadIdx.x, A = T * F;
     for (int i = tid; i < A; i += TD_THREADS) {
@@ -279,8 +291,7 @@ __device__ void masked_gaussian(const float *data, const uint8_t *flags, int T, 
         out[i] = flags[i] ? 0.0f : data[i];
     }
     __syncthreads();
-    box_filter_2d(weight, T, F, r_t, r_f, pad);
-    box_filter_2d(out, T, F, r_t, r_f, pad);
+    box_filter_2d_pair(weight, out, T, F, r_t, r_f, pad, pad_n);
     for (int i = tid; i < A; i += TD_THREADS)
         out[i] = (weight[i] == 0.0f) ? __int_as_float(0x7fc00000) : __fdiv_rn(out[i], weight[i]);
     __syncthreads();
@@ -319,13 +330,13 @@ __device__ void interpolate_row(float *row, int n)
 // twodflag.py:404-463.  flags_in is not modified; `work` receives the growing mask.
 __device__ void background2d(const TdArgs &a, const float *data, const uint8_t *flags_in, int T, int F,
                              const int *r_t, const int *r_f, float *bg, uint8_t *work, float *weight,
-                             float *pad, const SelectScratch &sc, uint32_t *s_count)
+                             float *pad, int64_t pad_n, const SelectScratch &sc, uint32_t *s_count)
 {
     const int tid = threadIdx.x, A = T * F;
     for (int i = tid; i < A; i += TD_THREADS) work[i] = flags_in[i] != 0;
     __syncthreads();
     for (int ef = a.p.background_iterations; ef >= 1; ef--) {
-        masked_gaussian(data, work, T, F, r_t ? r_t[ef] : 0, r_f[ef], bg, weight, pad);
+        masked_gaussian(data, work, T, F, r_t ? r_t[ef] : 0, r_f[ef], bg, weight, pad, pad_n);
         for (int c = 0; c < a.p.n_chunks; c++) {
             const int c0 = (int) a.p.chunk_ends[c], c1 = (int) a.p.chunk_ends[c + 1], cl = c1 - c0;
             for (int i = tid; i < T * cl; i += TD_THREADS) {
@@ -346,7 +357,7 @@ __device__ void background2d(const TdArgs &a, const float *data, const uint8_t *
             __syncthreads();
         }
     }
-    masked_gaussian(data, work, T, F, r_t ? r_t[1] : 0, r_f[1], bg, weight, pad);
+    masked_gaussian(data, work, T, F, r_t ? r_t[1] : 0, r_f[1], bg, weight, pad, pad_n);
     for (int t = tid; t < T; t += TD_THREADS) interpolate_row(bg + (int64_t) t * F, F);
     __syncthreads();
 }
@@ -438,7 +449,7 @@ __device__ void sum_threshold_freq(const TdArgs &a, const float *data, const uin
 }
 
 // ------------------------------------------------------------------ one baseline (twodflag.py:768-881)
-__global__ void __launch_bounds__(TD_THREADS)
+__global__ void __launch_bounds__(TD_THREADS, 4)
 twod_baseline_kernel(const TdArgs a)
 {
     __shared__ uint32_t s_hist[SELECT_HIST_WORDS];
@@ -471,14 +482,14 @@ twod_baseline_kernel(const TdArgs a)
         __syncthreads();
         // ---- background and SumThreshold of the spectrum
         background2d(a, b.spec_data, b.spec_flags, 1, F, nullptr, a.p.r_freq, b.spec_bg, b.spec_work,
-                     b.spec_weight, b.pad, sc, &s_count);
+                     b.spec_weight, b.pad, b.pad_n, sc, &s_count);
         for (int f = tid; f < F; f += TD_THREADS) b.spec_data[f] = __fsub_rn(b.spec_data[f], b.spec_bg[f]);
         __syncthreads();
         sum_threshold_freq(a, b.spec_data, b.spec_flags, 1, F, b.spec_out, b, sc, &s_count);
         for (int i = tid; i < A; i += TD_THREADS) b.flags[i] |= b.spec_out[i % F];
         __syncthreads();
         // ---- 2-D background
-        background2d(a, b.data, b.flags, T, F, a.p.r_time, a.p.r_freq, b.bg, b.work, b.weight, b.pad, sc, &s_count);
+        background2d(a, b.data, b.flags, T, F, a.p.r_time, a.p.r_freq, b.bg, b.work, b.weight, b.pad, b.pad_n, sc, &s_count);
         for (int i = tid; i < A; i += TD_THREADS) b.data[i] = __fsub_rn(b.data[i], b.bg[i]);
         __syncthreads();
         // ---- SumThreshold along time: one column per thread, one chunk [0, T)
