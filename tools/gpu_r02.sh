@@ -13,6 +13,6 @@ fi
 TK_OUT=$out/time_kernels_$tag.json timeout 600 python tools/time_kernels.py --reps 7 --chunks=0 2>&1 | grep -v "^$" > $out/time_kernels_$tag.log
 echo "time_kernels rc=$?"; cat $out/time_kernels_$tag.log
 if [ "$2" != "nobench" ]; then
-timeout 900 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err
+timeout 1200 python bench.py $BENCH_ARGS > $out/bench_$tag.json 2> $out/bench_$tag.err
 echo "bench rc=$?"; cat $out/bench_$tag.json; tail -5 $out/bench_$tag.err
 fi
