@@ -221,17 +221,18 @@ def measured_peak():
 
 
 def source_sha16() -> str:
-    """Fingerprint of the CUDA sources the library is built from."""
-    import glob
+    """Fingerprint of the CUDA sources the FLAGGER's kernels are built from (the helper
+    operations and the 2-D flagger are separate translation units and do not enter)."""
     import hashlib
 
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "katsdpsigproc_b200", "csrc")
-    names = sorted(glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh"))
-                   + glob.glob(os.path.join(csrc, "*.h")) + [os.path.join(csrc, "Makefile")])
+    names = ["Makefile", "common.cuh", "median13.cuh", "select.cuh", "tma.cuh", "bg13.cuh", "background.cu",
+             "madnz_stream.cuh", "madnz.cu", "threshold_tile.cuh", "threshold.cu", "flagger.cu",
+             "dataflow.h", "dataflow.cu"]
     for name in names:
-        with open(name, "rb") as f:
-            h.update(os.path.basename(name).encode() + b"\0" + f.read())
+        with open(os.path.join(csrc, name), "rb") as f:
+            h.update(name.encode() + b"\0" + f.read())
     return h.hexdigest()[:16]
 
 
