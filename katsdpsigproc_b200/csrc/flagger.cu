@@ -36,12 +36,28 @@ struct Layout {
 
 constexpr int MAX_LANES = 8;
 
-// Internal streams and events for running several chunks at a time (per device, created on
-// first use, never destroyed: they live as long as the process).
+// Internal streams and events for running several chunks at a time (per thread and device,
+// created on first use, released when the thread ends).
 struct LanePool {
     bool ready = false;
+    int device = -1;
     cudaStream_t stream[MAX_LANES];
     cudaEvent_t start, done[MAX_LANES];
+    // a thread that goes away gives its streams and events back (at process exit the runtime may
+    // already be unloading: the calls then fail harmlessly)
+    ~LanePool()
+    {
+        if (!ready) return;
+        int current = 0;
+        if (cudaGetDevice(&current) != cudaSuccess) return;
+        if (cudaSetDevice(device) != cudaSuccess) return;
+        for (int i = 0; i < MAX_LANES; i++) {
+            cudaStreamDestroy(stream[i]);
+            cudaEventDestroy(done[i]);
+        }
+        cudaEventDestroy(start);
+        cudaSetDevice(current);
+    }
 };
 
 int get_pool(LanePool **out)
@@ -57,6 +73,7 @@ int get_pool(LanePool **out)
             KSP_CUDA(cudaEventCreateWithFlags(&pool.done[i], cudaEventDisableTiming));
         }
         KSP_CUDA(cudaEventCreateWithFlags(&pool.start, cudaEventDisableTiming));
+        pool.device = dev;
         pool.ready = true;
     }
     *out = &pool;

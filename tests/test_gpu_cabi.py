@@ -297,6 +297,35 @@ def test_flagger_fused_many_windows(abs_mode):
     assert flags.any()
 
 
+def test_threshold_sum_deep_dips_next_to_marginal_wide_features():
+    """The filters of the threshold kernel must stay sound when a run holds large NEGATIVE
+    deviations (dropped samples on a bright band: dev = -median, far beyond the threshold in
+    magnitude): the bound on the sum of the positive samples is computed from two rounded sums and
+    its slack has to scale with sum |u|.  Wide features (16..64 channels) whose window sums sit
+    within ~1e-5 of firing, placed right next to such dips, must be flagged exactly as the
+    contract flags them."""
+    rs = np.random.RandomState(31)
+    channels, baselines = 4096, 48
+    dev = (rs.standard_normal((channels, baselines)) * 0.05).astype(np.float32)
+    noise = np.full(baselines, 1.0, np.float32)
+    n_sigma, rho, n_windows = 4.0, 1.2, 7
+    fired = 0
+    for b in range(baselines):
+        for k in range(12):
+            w = int(rs.choice([16, 32, 64]))
+            c0 = int(rs.randint(200, channels - 200))
+            thr = np.float32(n_sigma * 1.0 * rho ** -int(np.log2(w)))
+            # a plateau whose mean is the window threshold times (1 +- a few 1e-6 .. 1e-4)
+            level = np.float32(thr * (1.0 + rs.choice([-1, 1]) * 10 ** rs.uniform(-5.5, -4.0)))
+            dev[c0:c0 + w, b] = level
+            # deep dips inside the same 32-channel runs, before and after the plateau
+            dev[c0 - rs.randint(2, 12), b] = np.float32(-rs.uniform(200.0, 5000.0))
+            dev[c0 + w + rs.randint(1, 10), b] = np.float32(-rs.uniform(200.0, 5000.0))
+    expect = check_sum(dev, noise, n_sigma, n_windows, rho)
+    fired = int(expect.sum())
+    assert 0 < fired < expect.size // 2          # some of the marginal windows fire, some do not
+
+
 def test_threshold_sum_nan_noise_and_ties():
     dev = np.ones((64, 3), np.float32)
     noise = np.array([np.nan, 1.0 / 11.0, -1.0], np.float32)
