@@ -615,7 +615,7 @@ def twodflag_block(context) -> dict:
     p = flagger._params(shape, True)
     lib = _capi.load()
     per_bl = int(lib.ksp_twodflag_scratch_bytes(byref(p), 1))
-    batch = max(1, min(shape[2], 4 * 148, (4 << 30) // per_bl))
+    batch = max(1, min(shape[2], int(lib.ksp_twodflag_resident_baselines()), (8 << 30) // per_bl))
     d_vis = accel.DeviceArray(context, vis.shape, vis.dtype)
     d_fl = accel.DeviceArray(context, vis.shape, np.uint8)
     d_out = accel.DeviceArray(context, vis.shape, np.uint8)

@@ -256,6 +256,13 @@ size_t ksp_twodflag_scratch_bytes(const ksp_twodflag_params *p, int64_t batch_ba
 int ksp_twodflag(void *stream, const ksp_twodflag_params *p, const void *data, const uint8_t *in_flags,
                  uint8_t *out_flags, void *scratch, size_t scratch_bytes, int64_t batch_baselines);
 
+/* Baselines the device works on at the same time: the batch size that fills it. */
+int ksp_twodflag_resident_baselines(void);
+/* Developer aid: SM clock cycles the first block spent in each phase of the ksp_twodflag launches
+ * since the last reset (synchronous; indices documented in csrc/twodflag.cu). */
+#define KSP_TWOD_PHASES 20
+int ksp_twodflag_phases(unsigned long long *out, int n, int reset);
+
 /* ------------------------------------------------------------------------
  * General-purpose operations that sit beside the RFI ones in the reference.
  * ---------------------------------------------------------------------- */

@@ -166,6 +166,8 @@ PROTOTYPES = {
         c_int, [c_void_p, POINTER(FlaggerParams), c_void_p, POINTER(ctypes.c_ulonglong), c_int]),
     "ksp_flagger_is_dataflow": (c_int, [POINTER(FlaggerParams)]),
     "ksp_twodflag_scratch_bytes": (c_size_t, [POINTER(TwodflagParams), c_int64]),
+    "ksp_twodflag_resident_baselines": (c_int, []),
+    "ksp_twodflag_phases": (c_int, [POINTER(ctypes.c_ulonglong), c_int, c_int]),
     "ksp_twodflag": (
         c_int,
         [c_void_p, POINTER(TwodflagParams), c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_int64],

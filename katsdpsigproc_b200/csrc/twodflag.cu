@@ -8,10 +8,26 @@
 // cumulative sums of the SumThreshold) and on which intermediate is float32, so this file keeps
 // every such recurrence serial along its axis, in the reference's order and precision, and takes
 // its parallelism from everything the reference loops over independently: baselines (one
-// 256-thread block per baseline, blocks persistent over the batch), and inside a baseline the
-// columns of a time-axis recurrence, the rows (x frequency chunks) of a frequency-axis one.
-// oracle/twodflag_numpy.py states the same arithmetic in numpy and is pinned bit for bit against
-// the reference; the tests compare this file's flags with both.
+// 128-thread block per baseline, 8 blocks per SM, persistent over the batch), and inside a
+// baseline the columns of a time-axis recurrence, the rows (x frequency chunks) of a
+// frequency-axis one.  What changed against a line-by-line restatement is WHERE the recurrences
+// keep their state:
+//
+//   * box filters (twodflag.py:255-309): the reference runs four in-place passes over a padded
+//     copy of the line.  Pass p at position i reads only what pass p - 1 left at i .. i + 2 r, so
+//     the four passes are chained here as four stages of ONE sweep over the line, each stage
+//     with its float64 running sum in a register and its last 2 r inputs in a shared-memory
+//     ring; the line is read once and written once (frequency axis: through a transposing tile,
+//     128-byte rows of 32 lines at a time; time axis: directly, neighbouring threads hold
+//     neighbouring columns).  Same additions, same order, same float32 roundings between passes.
+//   * SumThreshold (twodflag.py:493-560): one sweep per window size, the last w + 1 cumulative
+//     sums in a shared-memory ring, flags as bit masks; "every hit flags the w samples of its
+//     window" becomes "sample k is flagged if any of the last w hits fired", a shift register.
+//   * medians (thresholds per row and chunk, MAD per chunk): exact radix select by ONE warp per
+//     set, the warps of a block working on different sets.
+//
+// oracle/twodflag_numpy.py states the reference's arithmetic in numpy and is pinned bit for bit
+// against the reference; the tests compare this file's flags with both.
 //
 // Three launches per batch of baselines:
 //   twod_average_kernel   (time, freq, baseline) input -> baseline-major averaged magnitudes + flags
@@ -26,9 +42,14 @@ namespace {
 
 using namespace ksp;
 
-constexpr int TD_THREADS = 256;
+constexpr int TD_THREADS = 128;
+constexpr int TD_WARPS = TD_THREADS / 32;
+constexpr int TD_BLOCKS_PER_SM = 8;
+constexpr int TD_SMEM_WORDS = 5120;          // 20 KB of rings / tiles per block
+constexpr int TD_TILE_WORDS = 32 * 33;       // transposing tile of the frequency-axis box filter
 constexpr int TD_PASSES = 4;                 // box filters per Gaussian (reference default, twodflag.py:313)
 constexpr double TD_MAD_NORMAL = 1.4826;     // rfi/__init__.py:31
+constexpr unsigned FULL = 0xffffffffu;
 
 struct TdArgs {
     ksp_twodflag_params p;
@@ -37,18 +58,29 @@ struct TdArgs {
     uint8_t *out_flags;          // same shape
     int64_t bl0, nb;             // batch of baselines
     int a_freq;                  // averaged channels
-    int max_rt, max_rf;          // largest box radii (they size the padded work array)
-    int max_wf;                  // largest frequency window
+    int max_rt, max_rf;          // largest box radii
+    int max_wt, max_wf;          // largest windows
+    int max_cl;                  // longest frequency chunk
+    int big_radius;              // a box radius too large for the shared-memory rings: in-place fallback
     char *scratch;
     size_t per_bl;               // scratch bytes per baseline
 };
 
+// Cycles block 0 spent in each phase of the launches since the last reset (ksp_twodflag_phases):
+// 0 spectrum median, 1 spectrum Gaussians, 2 spectrum MAD, 3 spectrum interpolation,
+// 4 spectrum thresholds, 5 spectrum SumThreshold, 6 2-D Gaussians, 7 2-D MAD, 8 2-D interpolation,
+// 9 SumThreshold in time, 10 thresholds per row and chunk, 11 SumThreshold in frequency,
+// 12 combination, 13 un-averaging and fill rules, 15 elementwise steps in between; inside the
+// Gaussians: 16 time-axis box passes, 17 frequency-axis box passes, 18 masking and normalisation.
+__device__ unsigned long long td_phase[KSP_TWOD_PHASES];
 // ---- per-baseline scratch layout (A = n_time * a_freq elements)
 struct TdBuffers {
-    float *data, *bg, *weight, *pad, *vals;
-    int64_t pad_n;               // floats per work area of `pad` (there are two)
+    float *data, *bg, *weight, *vals;
+    float *pad;                  // in-place work areas of the large-radius fallback (two of pad_n floats)
+    int64_t pad_n;
     float *spec_data, *spec_bg, *spec_weight;
-    uint8_t *flags, *work, *tfl, *ffl, *pos, *neg, *hp, *hn, *spec_flags, *spec_work, *spec_out, *comb;
+    uint8_t *flags, *work, *tfl, *ffl, *spec_flags, *spec_work, *spec_out, *comb;
+    uint32_t *posw, *negw;       // SumThreshold bit masks, [word][line]
     uint8_t *outb;               // (n_time, n_freq) flags of this baseline at the original resolution
     uint8_t *row_full, *col_full; // n_time, n_freq
     float *thr;                  // thresholds per (row, chunk)
@@ -56,355 +88,884 @@ struct TdBuffers {
 
 __host__ __device__ inline size_t td_align(size_t x) { return (x + 255) / 256 * 256; }
 
-__host__ __device__ inline size_t td_row_work(const ksp_twodflag_params &p, int a_freq, int max_wf);
-
-__host__ __device__ inline size_t td_layout(const ksp_twodflag_params &p, int a_freq, int max_r_t, int max_r_f,
-                                            int max_wf, char *base, TdBuffers *b)
+// words of one SumThreshold bit mask: the larger of the frequency-axis lines (every (row, chunk)
+// has its slice of chunk + 2 (largest window - 1) samples) and the time-axis ones (one per column)
+__host__ __device__ inline size_t td_mask_words(const TdArgs &a)
 {
-    const size_t T = (size_t) p.n_time, F = (size_t) a_freq, A = T * F;
-    const size_t pad_t = (T + (size_t) max_r_t * TD_PASSES) * F, pad_f = T * (F + (size_t) max_r_f * TD_PASSES);
-    const size_t pad_n = pad_t > pad_f ? pad_t : pad_f;
+    const size_t T = (size_t) a.p.n_time, F = (size_t) a.a_freq;
+    const size_t wf = ((size_t) a.max_cl + 2 * (size_t) a.max_wf + 31) / 32 * T * (size_t) a.p.n_chunks;
+    const size_t wt = (T + 31) / 32 * F;
+    return wf > wt ? wf : wt;
+}
+
+__host__ __device__ inline size_t td_layout(const TdArgs &a, char *base, TdBuffers *b)
+{
+    const size_t T = (size_t) a.p.n_time, F = (size_t) a.a_freq, A = T * F;
+    size_t pad_n = 0;
+    if (a.big_radius) {
+        const size_t pad_t = (T + (size_t) a.max_rt * TD_PASSES) * F, pad_f = T * (F + (size_t) a.max_rf * TD_PASSES);
+        pad_n = pad_t > pad_f ? pad_t : pad_f;
+    }
     size_t off = 0;
     auto take = [&](size_t bytes) { size_t o = off; off += td_align(bytes); return base ? base + o : (char *) nullptr; };
     float *f_data = (float *) take(A * 4), *f_bg = (float *) take(A * 4), *f_w = (float *) take(A * 4);
-    float *f_pad = (float *) take(2 * pad_n * 4), *f_vals = (float *) take(A * 4);
+    float *f_vals = (float *) take(A * 4), *f_pad = (float *) take(2 * pad_n * 4);
     float *s_data = (float *) take(F * 4), *s_bg = (float *) take(F * 4), *s_w = (float *) take(F * 4);
-    const size_t W = T * td_row_work(p, a_freq, max_wf);       // >= A
-    uint8_t *u[12];
+    uint8_t *u[8];
     for (int i = 0; i < 4; i++) u[i] = (uint8_t *) take(A);
-    for (int i = 4; i < 8; i++) u[i] = (uint8_t *) take(W);    // pos, neg, hits
-    for (int i = 8; i < 11; i++) u[i] = (uint8_t *) take(F);
-    u[11] = (uint8_t *) take(A);
-    uint8_t *outb = (uint8_t *) take(T * (size_t) p.n_freq);
-    uint8_t *row_full = (uint8_t *) take(T), *col_full = (uint8_t *) take((size_t) p.n_freq);
-    float *thr = (float *) take((T + 1) * (size_t) (p.n_chunks > 0 ? p.n_chunks : 1) * 4);
+    for (int i = 4; i < 7; i++) u[i] = (uint8_t *) take(F);
+    u[7] = (uint8_t *) take(A);
+    const size_t mw = td_mask_words(a);
+    uint32_t *posw = (uint32_t *) take(mw * 4), *negw = (uint32_t *) take(mw * 4);
+    uint8_t *outb = (uint8_t *) take(T * (size_t) a.p.n_freq);
+    uint8_t *row_full = (uint8_t *) take(T), *col_full = (uint8_t *) take((size_t) a.p.n_freq);
+    float *thr = (float *) take((T + 1) * (size_t) (a.p.n_chunks > 0 ? a.p.n_chunks : 1) * 4);
     if (b) {
-        b->data = f_data; b->bg = f_bg; b->weight = f_w; b->pad = f_pad; b->vals = f_vals;
+        b->data = f_data; b->bg = f_bg; b->weight = f_w; b->vals = f_vals; b->pad = f_pad;
         b->pad_n = (int64_t) pad_n;
         b->spec_data = s_data; b->spec_bg = s_bg; b->spec_weight = s_w;
-        b->flags = u[0]; b->work = u[1]; b->tfl = u[2]; b->ffl = u[3]; b->pos = u[4]; b->neg = u[5];
-        b->hp = u[6]; b->hn = u[7]; b->spec_flags = u[8]; b->spec_work = u[9]; b->spec_out = u[10];
-        b->comb = u[11]; b->outb = outb; b->thr = thr; b->row_full = row_full; b->col_full = col_full;
+        b->flags = u[0]; b->work = u[1]; b->tfl = u[2]; b->ffl = u[3];
+        b->spec_flags = u[4]; b->spec_work = u[5]; b->spec_out = u[6]; b->comb = u[7];
+        b->posw = posw; b->negw = negw;
+        b->outb = outb; b->thr = thr; b->row_full = row_full; b->col_full = col_full;
     }
     return off;
 }
 
-__host__ __device__ inline size_t td_row_work(const ksp_twodflag_params &p, int a_freq, int max_wf)
-{
-    // work bytes of one row of a frequency-axis SumThreshold: every (row, chunk) has its own
-    // padded slice (chunk + 2 (largest window - 1))
-    return (size_t) a_freq + (size_t) p.n_chunks * 2 * (size_t) max_wf;
-}
-
 __device__ __forceinline__ void td_buffers(const TdArgs &a, int64_t blr, TdBuffers *b)
 {
-    td_layout(a.p, a.a_freq, a.max_rt, a.max_rf, a.max_wf, a.scratch + (size_t) blr * a.per_bl, b);
+    td_layout(a, a.scratch + (size_t) blr * a.per_bl, b);
 }
 
 // ------------------------------------------------------------------ averaging (twodflag.py:68-116)
+// Block = 32 baselines x 32 averaged channels of one dump: the input is read with the baseline
+// fastest (its layout), the per-baseline arrays are written with the channel fastest (theirs).
 template <bool COMPLEX>
 __global__ void __launch_bounds__(256)
 twod_average_kernel(const TdArgs a)
 {
-    // thread <-> (baseline of the batch, time, averaged channel); baseline fastest so that the
-    // reads of a warp are contiguous
-    const int64_t total = a.nb * a.p.n_time * a.a_freq;
-    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int64_t blr = i % a.nb;
-    const int64_t rest = i / a.nb;
-    const int jo = (int) (rest % a.a_freq);
-    const int t = (int) (rest / a.a_freq);
+    __shared__ float s_val[32][33];
+    __shared__ uint8_t s_flag[32][33];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int64_t bl_tile = (int64_t) blockIdx.x * 32;
+    const int f_tile = (int) blockIdx.y * 32;
+    const int t = (int) blockIdx.z;
     const int factor = a.p.average_freq;
-    float sum = 0.0f;
-    int count = 0;
-    for (int j = jo * factor; j < (jo + 1) * factor && j < a.p.n_freq; j++) {
-        const int64_t idx = ((int64_t) t * a.p.n_freq + j) * a.p.n_bl + a.bl0 + blr;
-        float mag;
-        if (COMPLEX) {
-            const float2 v = reinterpret_cast<const float2 *>(a.data)[idx];
-            // numba's abs(complex64): the correctly rounded hypot
-            mag = (isnan(v.x) || isnan(v.y)) ? __int_as_float(0x7fc00000)
-                                             : abs_slow(fabsf(v.x), fabsf(v.y), KSP_ABS_HYPOT);
-        } else {
-            mag = fabsf(reinterpret_cast<const float *>(a.data)[idx]);
+    const int64_t blr = bl_tile + lane;
+    for (int fo = wrp; fo < 32; fo += 8) {
+        const int jo = f_tile + fo;
+        float sum = 0.0f;
+        int count = 0;
+        if (blr < a.nb && jo < a.a_freq) {
+            for (int j = jo * factor; j < (jo + 1) * factor && j < a.p.n_freq; j++) {
+                const int64_t idx = ((int64_t) t * a.p.n_freq + j) * a.p.n_bl + a.bl0 + blr;
+                float mag;
+                if (COMPLEX) {
+                    const float2 v = __ldg(reinterpret_cast<const float2 *>(a.data) + idx);
+                    // numba's abs(complex64): the correctly rounded hypot
+                    mag = (isnan(v.x) || isnan(v.y)) ? __int_as_float(0x7fc00000)
+                                                     : abs_slow(fabsf(v.x), fabsf(v.y), KSP_ABS_HYPOT);
+                } else {
+                    mag = fabsf(__ldg(reinterpret_cast<const float *>(a.data) + idx));
+                }
+                if (!__ldg(a.in_flags + idx) && !isnan(mag)) {
+                    sum = __fadd_rn(sum, mag);
+                    count++;
+                }
+            }
         }
-        if (!a.in_flags[idx] && !isnan(mag)) {
-            sum = __fadd_rn(sum, mag);
-            count++;
+        s_val[fo][lane] = count ? __fdiv_rn(sum, (float) count) : 0.0f;
+        s_flag[fo][lane] = count == 0;
+    }
+    __syncthreads();
+    const int jo = f_tile + lane;
+    for (int bo = wrp; bo < 32; bo += 8) {
+        const int64_t bl = bl_tile + bo;
+        if (bl < a.nb && jo < a.a_freq) {
+            TdBuffers b;
+            td_buffers(a, bl, &b);
+            const size_t o = (size_t) t * a.a_freq + jo;
+            b.data[o] = s_val[lane][bo];
+            b.flags[o] = s_flag[lane][bo];
         }
     }
-    TdBuffers b;
-    td_buffers(a, blr, &b);
-    const size_t o = (size_t) t * a.a_freq + jo;
-    b.data[o] = count ? __fdiv_rn(sum, (float) count) : 0.0f;
-    b.flags[o] = count == 0;
 }
+
+// ------------------------------------------------------------------ shared state of twod_baseline_kernel
+// The phases below are separate (non-inlined) functions so that each gets its own register
+// allocation; what they share lives here instead of in arguments.
+__shared__ TdArgs s_a;                                   // the launch arguments
+__shared__ TdBuffers s_b;                                // scratch arrays of the block's current baseline
+__shared__ __align__(16) float s_sm[TD_SMEM_WORDS];      // rings and tiles
+__shared__ uint32_t s_whist[TD_WARPS * 256];             // one 256-bin histogram per warp
+__shared__ long long s_last;                             // td_mark's clock
+
+__device__ __forceinline__ void td_mark(int k)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const long long now = clock64();
+        td_phase[k] += (unsigned long long) (now - s_last);
+        s_last = now;
+    }
+}
+
+// Thread number with the warps rotated by a per-block amount.  The phases that cannot use every
+// warp (a box filter along frequency has 2 T lines) hand their work to the first warps IN THIS
+// NUMBERING: warp w of a block always runs on scheduler w mod 4 of its SM, and with the plain
+// numbering the working warps of all the blocks of an SM would queue for the conversion pipe of
+// one scheduler while the other three sat idle.
+__device__ __forceinline__ int td_vtid()
+{
+    const unsigned rot = (blockIdx.x * 0x9E3779B1u) >> 30;
+    return (int) (((threadIdx.x >> 5) + rot) & (TD_WARPS - 1)) * 32 + (int) (threadIdx.x & 31);
+}
+static_assert(TD_WARPS == 4, "td_vtid rotates four warps");
 
 // ------------------------------------------------------------------ small helpers
-__device__ __forceinline__ float median_sorted_f32(const float *s, int n)
+__device__ __forceinline__ float td_nan() { return __int_as_float(0x7fc00000); }
+
+__device__ __forceinline__ float median_sorted_f32(const float *s, int64_t stride, int n)
 {
-    if (n & 1) return s[n / 2];
-    return __fmul_rn(__fadd_rn(s[n / 2 - 1], s[n / 2]), 0.5f);
+    if (n & 1) return s[(int64_t) (n / 2) * stride];
+    return __fmul_rn(__fadd_rn(s[(int64_t) (n / 2 - 1) * stride], s[(int64_t) (n / 2) * stride]), 0.5f);
 }
 
-// insertion sort of a thread-private segment (n is a few hundred at most: the time axis)
-__device__ void sort_small(float *v, int n)
+// insertion sort of a thread-private strided segment (the time axis of one column; neighbouring
+// threads hold neighbouring columns, so the accesses of a warp coalesce)
+__device__ void sort_small(float *v, int64_t stride, int n)
 {
     for (int i = 1; i < n; i++) {
-        const float x = v[i];
+        const float x = v[(int64_t) i * stride];
         int j = i - 1;
-        while (j >= 0 && v[j] > x) {
-            v[j + 1] = v[j];
+        while (j >= 0 && v[(int64_t) j * stride] > x) {
+            v[(int64_t) (j + 1) * stride] = v[(int64_t) j * stride];
             j--;
         }
-        v[j + 1] = x;
+        v[(int64_t) (j + 1) * stride] = x;
     }
 }
 
-// Median of |x| over the unflagged elements of an index set, by the whole block (exact radix
-// select on the float bit patterns).  key_at(i) returns KEY_SKIP for flagged elements.  NaN if none.
-template <typename KeyAt>
-__device__ float block_median_abs(const KeyAt &key_at, int n, const SelectScratch &sc, uint32_t *s_count)
+// Median of the unflagged samples of one column (values at x[t * stride], flags at fl[t * stride],
+// t < T <= N) in registers: flagged samples become +inf, Batcher's odd-even merge sort of N values
+// with every index known at compile time, then the middle of the n unflagged ones.  ABS: of |x|.
+// n == 0: returns NaN and *count = 0.
+template <int N, bool ABS>
+__device__ __forceinline__ float column_median(const float *x, const uint8_t *fl, int64_t stride, int T, int *count)
 {
-    const int tid = threadIdx.x;
-    if (tid == 0) *s_count = 0u;
-    __syncthreads();
-    uint32_t mine = 0;
-    for (int i = tid; i < n; i += TD_THREADS) mine += key_at(i) != KEY_SKIP;
-    mine = __reduce_add_sync(0xffffffffu, mine);
-    if ((tid & 31) == 0 && mine) atomicAdd(s_count, mine);
-    __syncthreads();
-    const uint32_t n_valid = *s_count;
-    __syncthreads();
-    if (n_valid == 0) return __int_as_float(0x7fc00000);
-    const uint32_t k = (n_valid - 1) >> 1;
-    const uint32_t lo = block_radix_select<TD_THREADS>(key_at, n, k, sc);
+    float v[N];
+    int n = 0;
+#pragma unroll
+    for (int t = 0; t < N; t++) {
+        float val = __int_as_float(0x7f800000);
+        if (t < T && !fl[(int64_t) t * stride]) {
+            val = x[(int64_t) t * stride];
+            if (ABS) val = fabsf(val);
+            n++;
+        }
+        v[t] = val;
+    }
+    *count = n;
+    if (n == 0) return td_nan();
+#pragma unroll
+    for (int p = 1; p < N; p <<= 1)
+#pragma unroll
+        for (int k = p; k >= 1; k >>= 1)
+#pragma unroll
+            for (int j = k % p; j <= N - 1 - k; j += 2 * k)
+#pragma unroll
+                for (int i = 0; i <= (k - 1 < N - j - k - 1 ? k - 1 : N - j - k - 1); i++)
+                    if ((i + j) / (2 * p) == (i + j + k) / (2 * p)) {
+                        const float lo = fminf(v[i + j], v[i + j + k]), hi = fmaxf(v[i + j], v[i + j + k]);
+                        v[i + j] = lo;
+                        v[i + j + k] = hi;
+                    }
+    const int hi_i = n >> 1, lo_i = (n - 1) >> 1;
+    float a = 0.0f, b = 0.0f;
+#pragma unroll
+    for (int t = 0; t < N; t++) {
+        if (t == lo_i) a = v[t];
+        if (t == hi_i) b = v[t];
+    }
+    return (n & 1) ? b : __fmul_rn(__fadd_rn(a, b), 0.5f);
+}
+
+// The same for any T: the samples are gathered into `work` (stride as the inputs) and sorted there.
+template <bool ABS>
+__device__ float column_median_any(const float *x, const uint8_t *fl, float *work, int64_t stride, int T, int *count)
+{
+    if (T <= 16) return column_median<16, ABS>(x, fl, stride, T, count);
+    if (T <= 32) return column_median<32, ABS>(x, fl, stride, T, count);
+    int n = 0;
+    for (int t = 0; t < T; t++)
+        if (!fl[(int64_t) t * stride]) {
+            const float val = x[(int64_t) t * stride];
+            work[(int64_t) (n++) * stride] = ABS ? fabsf(val) : val;
+        }
+    *count = n;
+    if (n == 0) return td_nan();
+    sort_small(work, stride, n);
+    return median_sorted_f32(work, stride, n);
+}
+
+__device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(FULL, v, d);
+        if (lane >= d) v += o;
+    }
+    return v;
+}
+
+// Median of the non-skipped keys of a set, by ONE warp: exact radix select on the bit patterns of
+// non-negative floats, 4 passes of 8 bits with a 256-bin histogram of the warp's own, then (even
+// counts) one pass for the next key above; float32 mean of the two middle values as numba's
+// np.median of float32.  key_at(i), i < n, returns KEY_SKIP for elements that take no part.
+// NaN if the set is empty.  All lanes return the same value.
+template <typename KeyAt>
+__device__ float warp_median(const KeyAt &key_at, int n, uint32_t *hist, int lane)
+{
+    uint32_t prefix = 0, prefix_mask = 0, rank = 0, n_valid = 0;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int bin = lane; bin < 256; bin += 32) hist[bin] = 0u;
+        __syncwarp();
+        for (int i = lane; i < n; i += 128) {                      // four loads in flight per lane
+            uint32_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) k[u] = (i + 32 * u < n) ? key_at(i + 32 * u) : KEY_SKIP;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k[u] != KEY_SKIP && (k[u] & prefix_mask) == prefix) atomicAdd(&hist[(k[u] >> shift) & 0xffu], 1u);
+        }
+        __syncwarp();
+        uint32_t c[8], tot = 0;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            c[j] = hist[8 * lane + j];
+            tot += c[j];
+        }
+        const uint32_t incl = warp_scan_incl(tot, lane), excl = incl - tot;
+        if (shift == 24) {
+            n_valid = __shfl_sync(FULL, incl, 31);
+            if (n_valid == 0) return td_nan();                      // warp-uniform
+            rank = (n_valid - 1) >> 1;
+        }
+        const bool mine = rank >= excl && rank < incl;
+        const int src = __ffs(__ballot_sync(FULL, mine)) - 1;
+        uint32_t bin = 0, r_in = 0;
+        if (mine) {
+            uint32_t e = excl;
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (rank >= e && rank < e + c[j]) {
+                    bin = 8u * (uint32_t) lane + j;
+                    r_in = rank - e;
+                }
+                e += c[j];
+            }
+        }
+        bin = __shfl_sync(FULL, bin, src);
+        rank = __shfl_sync(FULL, r_in, src);
+        prefix |= bin << shift;
+        prefix_mask |= 0xffu << shift;
+        __syncwarp();
+    }
+    const uint32_t lo = prefix;
     uint32_t hi = lo;
     if (!(n_valid & 1u)) {
-        uint32_t next, count_le;
-        block_next_above<TD_THREADS>(key_at, n, lo, next, count_le, sc);
-        if (count_le < k + 2) hi = next;
+        uint32_t best = KEY_SKIP, cnt = 0;
+        for (int i = lane; i < n; i += 128) {
+            uint32_t k[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) k[u] = (i + 32 * u < n) ? key_at(i + 32 * u) : KEY_SKIP;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (k[u] != KEY_SKIP) {
+                    if (k[u] <= lo) cnt++;
+                    else best = min(best, k[u]);
+                }
+        }
+        best = __reduce_min_sync(FULL, best);
+        cnt = __reduce_add_sync(FULL, cnt);
+        if (cnt < ((n_valid - 1) >> 1) + 2) hi = best;              // rank k + 1 is the next distinct key
     }
     const float a = __uint_as_float(lo), b = __uint_as_float(hi);
     return lo == hi ? a : __fmul_rn(__fadd_rn(a, b), 0.5f);
 }
 
 // ------------------------------------------------------------------ box filter (twodflag.py:255-309)
-// One line: n samples at data[k * stride], work array padded[(k) * pstride] of n + r * K floats.
-// float64 running sum, float32 stores, in the reference's order; result / float32(d^K).
-__device__ void box_line(const float *data, int64_t stride, float *padded, int64_t pstride, int n, int r,
-                         float *out, int64_t ostride, float divisor)
+// The reference pads the line with 4 r zeros in front (padded = [0] * 4 r + line, len = n + 4 r;
+// beyond the end counts as zero too) and runs pass p = 1 .. 4 in place:
+//     s = sum(padded[0 : 2 r]);  for i < len:  s += padded[i + 2 r];  out = float32(s);
+//                                              s -= padded[i];  padded[i] = out
+// (its start / stop bookkeeping only skips positions whose inputs are known zeros), then returns
+// padded[0 : n] / float32((2 r + 1)^4).  Pass p at position i needs pass p - 1 at i .. i + 2 r
+// only, so the passes run here as four stages of one sweep: at step k (k = 0 .. len - 1) stage 1
+// takes line[k] (its index 4 r + k), stage 2 the value stage 1 has just produced (index 2 r + k),
+// stage 3 what stage 2 produced (index k), stage 4 what stage 3 produced (index k - 2 r), and
+// the result for line position k - 4 r leaves stage 4.  Each stage keeps its float64 sum and a
+// ring of its last 2 r inputs; all four rings turn together, so one slot number serves them.
+// The rings of stages 1 and 2 start as zeros (the padding), those of 3 and 4 are filled while
+// these stages sum their first 2 r inputs.
+// Inside one thread the stages are SKEWED by one step each: iteration `it` runs stage 1 at step
+// it, stage 2 at step it - 1 (on what stage 1 produced in the previous iteration), stage 3 at
+// step it - 2, stage 4 at step it - 3.  Nothing in an iteration then waits for anything else in
+// it - four independent dependency chains instead of one four times as long.
+// Two arithmetics.  BoxF64: the reference's - float64 sums, float32 between the stages.
+// BoxInt: the same sums as 32-bit integers, for lines whose samples are 0 or 1 (the weights of a
+// masked filter): every intermediate is an integer below (2 r + 1)^4, so for r <= 31 it is below
+// 2^24 and both the float64 sums and their float32 roundings are exact - integer adds give the
+// same bits without touching the float64 and conversion pipes.
+struct BoxF64 {
+    typedef double Sum;
+    typedef float Val;
+    static __device__ __forceinline__ double add(double s, float v) { return __dadd_rn(s, (double) v); }
+    static __device__ __forceinline__ double sub(double s, float v) { return __dsub_rn(s, (double) v); }
+    static __device__ __forceinline__ float round(double s) { return (float) s; }
+    static __device__ __forceinline__ float load(const float *p) { return *p; }
+    static __device__ __forceinline__ void store(float *p, float v) { *p = v; }
+    static __device__ __forceinline__ float from_input(float v) { return v; }
+    static __device__ __forceinline__ float to_float(float v) { return v; }
+};
+struct BoxInt {
+    typedef int Sum;
+    typedef int Val;
+    static __device__ __forceinline__ int add(int s, int v) { return s + v; }
+    static __device__ __forceinline__ int sub(int s, int v) { return s - v; }
+    static __device__ __forceinline__ int round(int s) { return s; }
+    static __device__ __forceinline__ int load(const float *p) { return __float_as_int(*p); }
+    static __device__ __forceinline__ void store(float *p, int v) { *p = __int_as_float(v); }
+    static __device__ __forceinline__ int from_input(float v) { return v != 0.0f; }
+    static __device__ __forceinline__ float to_float(int v) { return (float) v; }
+};
+constexpr int TD_INT_RADIUS = 31;                 // (2 * 31 + 1)^4 < 2^24
+
+// Inside one thread the stages are SKEWED by one step each: iteration `it` runs stage 1 at step
+// it, stage 2 at step it - 1 (on what stage 1 produced in the previous iteration), stage 3 at
+// step it - 2, stage 4 at step it - 3.  Nothing in an iteration then waits for anything else in
+// it - four independent dependency chains instead of one four times as long.
+template <typename A>
+struct BoxState {
+    typename A::Sum s1, s2, s3, s4;
+    typename A::Val e1, e2, e3;   // what stages 1 - 3 produced in the previous iteration
+};
+
+// rp: this line's slot (it mod 2 r) of the stage-1 ring; the other stages' rings follow at
+// multiples of `pitch` (all four must be readable: zero the lot before the first iteration).
+// Returns true when `out` holds the unnormalised result for line position it - 3 - 2 * r2.  Call
+// for it = 0 .. n + 2 * r2 + 2.
+// The body is branch-free (selects and one predicated result): the scheduler issues in order, and
+// only inside one basic block can the four chains overlap.  Stages that have not started yet see
+// zeros (e1 .. e3 start as 0, the rings of stages 1 and 2 too), for which every operation below
+// is a no-op, so only four conditions remain.
+template <typename A>
+__device__ __forceinline__ bool box_iter(BoxState<A> &st, float *rp, int pitch, int it, int n, int r2, float v_in,
+                                         float &out)
 {
-    const int K = TD_PASSES;
-    const int padding = r * K, len = n + padding;
-    for (int i = 0; i < padding; i++) padded[(int64_t) i * pstride] = 0.0f;
-    for (int i = 0; i < n; i++) padded[(int64_t) (padding + i) * pstride] = data[(int64_t) i * stride];
-    int prev_start = padding;
-    for (int p = 1; p <= K; p++) {
-        double s = 0.0;
-        int start = padding - 2 * r * p;
-        int stop = start + n + 2 * padding;
-        start = max(start, 0);
-        stop = min(stop, len);
-        const int tail = min(stop, len - 2 * r);
-        for (int i = prev_start; i < min(start + 2 * r, len); i++) s += (double) padded[(int64_t) i * pstride];
-        // Step i reads padded[i + 2 r] and padded[i] and writes padded[i]: every read is of an
-        // element no earlier step wrote, so the loads of a batch of steps are issued together and
-        // only the two float64 additions per step stay serial.
-        int i = start;
-        for (; i + 8 <= tail; i += 8) {
-            float in[8], prev[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                in[k] = padded[(int64_t) (i + k + 2 * r) * pstride];
-                prev[k] = padded[(int64_t) (i + k) * pstride];
-            }
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                s += (double) in[k];
-                padded[(int64_t) (i + k) * pstride] = (float) s;
-                s -= (double) prev[k];
-            }
-        }
-        for (; i < tail; i++) {
-            s += (double) padded[(int64_t) (i + 2 * r) * pstride];
-            const float prev = padded[(int64_t) i * pstride];
-            padded[(int64_t) i * pstride] = (float) s;
-            s -= (double) prev;
-        }
-        for (int i = tail; i < stop; i++) {
-            const float prev = padded[(int64_t) i * pstride];
-            padded[(int64_t) i * pstride] = (float) s;
-            s -= (double) prev;
-        }
-        prev_start = start;
-    }
-    for (int i = 0; i < n; i++) out[(int64_t) i * ostride] = __fdiv_rn(padded[(int64_t) i * pstride], divisor);
+    typedef typename A::Sum Sum;
+    typedef typename A::Val Val;
+    const Val v = A::from_input(v_in);
+    const bool c1 = it < n;                 // stage 1 still has input
+    const bool c2 = it - 1 < n + r2;        // stage 2 still has input
+    const bool d3 = it - 2 >= r2;           // stage 3 has summed its first 2 r inputs: it produces and pops
+    const bool d4 = it - 3 >= 2 * r2;       // stage 4 likewise
+    const Val old1 = A::load(rp), old2 = A::load(rp + pitch), old3 = A::load(rp + 2 * pitch),
+              old4 = A::load(rp + 3 * pitch);
+    // stage 4 at step it - 3, on what stage 3 produced in the previous iteration
+    const Sum s4a = A::add(st.s4, st.e3);
+    out = A::to_float(A::round(s4a));
+    const Sum s4b = A::sub(s4a, old4);
+    st.s4 = d4 ? s4b : s4a;
+    A::store(rp + 3 * pitch, st.e3);
+    // stage 3 at step it - 2
+    const Sum s3a = A::add(st.s3, st.e2);
+    const Val e3n = A::round(s3a);
+    const Sum s3b = A::sub(s3a, old3);
+    st.e3 = d3 ? e3n : st.e3;
+    st.s3 = d3 ? s3b : s3a;
+    A::store(rp + 2 * pitch, st.e2);
+    // stage 2 at step it - 1
+    const Sum s2a0 = A::add(st.s2, st.e1);
+    const Sum s2a = c2 ? s2a0 : st.s2;
+    st.e2 = A::round(s2a);
+    st.s2 = A::sub(s2a, old2);
+    A::store(rp + pitch, st.e1);
+    // stage 1 at step it
+    const Sum s1a0 = A::add(st.s1, v);
+    const Sum s1a = c1 ? s1a0 : st.s1;
+    st.e1 = A::round(s1a);
+    st.s1 = A::sub(s1a, old1);
+    A::store(rp, v);
+    return d4;
 }
 
 // float32(2 r + 1) ** K as numba evaluates it: binary exponentiation in float32 (K = 4: the
 // square of the square)
 __device__ __forceinline__ float box_divisor(int r)
 {
+    static_assert(sizeof(TdArgs) % 4 == 0, "copied by words");
     static_assert(TD_PASSES == 4, "square of the square");
     const float d = (float) (2 * r + 1);
     const float d2 = __fmul_rn(d, d);
     return __fmul_rn(d2, d2);
 }
 
-// In-place 2-D filter of TWO arrays (T x F each; they are independent, so their lines run side
-// by side): time axis (one thread per array and column), then frequency (per array and row).
-// pad: two work areas of pad_n floats.
-__device__ void box_filter_2d_pair(float *arr0, float *arr1, int T, int F, int r_t, int r_f, float *pad,
-                                   int64_t pad_n)
+// Lines of a ring-based pass that fit the shared memory: a multiple of 32 when at least 32 fit.
+__device__ __forceinline__ int td_lines_that_fit(int words_available, int words_per_line, int most)
 {
-    const int tid = threadIdx.x;
-    if (r_t > 0) {
+    int L = words_available / words_per_line;
+    if (L > most) L = most;
+    if (L >= 32) L &= ~31;
+    return L;
+}
+
+// Time axis of a masked filter: one thread per line - lines 0 .. F - 1 the weights of the
+// columns (1 where unflagged), lines F .. 2 F - 1 the data with flagged samples zeroed, both made
+// on the fly from `data` and `flags` - L lines at a time, results into weight / out.  The inputs
+// of the next eight iterations (and of the thread's next line) are requested before the current
+// eight are worked on: the arrays live in DRAM, and nothing else hides that latency.
+struct TimeLine {
+    const float *data;
+    const uint8_t *flags;
+    int T, F;
+    __device__ __forceinline__ void load8(int line, int t0, float (&v)[8]) const
+    {
+        const bool is_data = line >= F;
+        const int f = is_data ? line - F : line;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            float x = 0.0f;
+            if (t0 + k < T) {
+                const int64_t o = (int64_t) (t0 + k) * F + f;
+                x = is_data ? data[o] : 1.0f;
+                if (flags[o]) x = 0.0f;
+            }
+            v[k] = x;
+        }
+    }
+};
+
+template <typename A>
+__device__ __forceinline__ void box_time_line(const TimeLine &in, int line, float (&v)[8], float *dst, float *ring,
+                                              int L, int r2, float div)
+{
+    const int T = in.T, F = in.F, len = T + 2 * r2, pitch = r2 * L;
+    for (int s = 0; s < 4 * r2; s++) ring[s * L] = 0.0f;                  // all four rings (0 in either arithmetic)
+    BoxState<A> st = {0, 0, 0, 0, 0, 0, 0};
+    int slot = 0;
+    for (int it0 = 0; it0 < len + 3; it0 += 8) {
+        float v2[8];
+        if (it0 + 8 < T) {
+            in.load8(line, it0 + 8, v2);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 8; k++) v2[k] = 0.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int it = it0 + k;
+            if (it < len + 3) {
+                float o;
+                if (box_iter<A>(st, ring + slot * L, pitch, it, T, r2, v[k], o))
+                    dst[(int64_t) (it - 3 - 2 * r2) * F] = __fdiv_rn(o, div);
+                slot = (slot + 1 == r2) ? 0 : slot + 1;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = v2[k];
+    }
+}
+
+__device__ __noinline__ void box_time_pass(const float *__restrict__ data, const uint8_t *__restrict__ flags,
+                                           float *__restrict__ weight, float *__restrict__ out, int T, int F, int r)
+{
+    const int tid = td_vtid(), r2 = 2 * r;
+    const int L = td_lines_that_fit(TD_SMEM_WORDS, 4 * r2, TD_THREADS);
+    const float div = box_divisor(r);
+    const int lines = 2 * F;
+    const TimeLine in = {data, flags, T, F};
+    float nxt[8];
+    if (tid < L && tid < lines) in.load8(tid, 0, nxt);
+    for (int base = 0; base < lines; base += L) {
+        const int line = base + tid;
+        if (tid < L && line < lines) {
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = nxt[k];
+            if (line + L < lines) in.load8(line + L, 0, nxt);             // the next round's first inputs
+            float *ring = s_sm + tid;
+            if (line < F) {
+                if (r <= TD_INT_RADIUS) box_time_line<BoxInt>(in, line, v, weight + line, ring, L, r2, div);
+                else box_time_line<BoxF64>(in, line, v, weight + line, ring, L, r2, div);
+            } else {
+                box_time_line<BoxF64>(in, line, v, out + (line - F), ring, L, r2, div);
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void cp_async4(float *smem_dst, const float *src, bool valid)
+{
+    const uint32_t d = (uint32_t) __cvta_generic_to_shared(smem_dst);
+    const int bytes = valid ? 4 : 0;                              // 0: nothing is read, the word is zero-filled
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
+}
+
+// Frequency axis of a masked filter.  A warp takes L <= 32 lines - pairs (weights of row t, data
+// of row t) - and moves them through 32 x 32 transposing tiles: rows of 128 bytes in (cp.async,
+// the next tile in flight while this one is worked on), lane <-> line inside.  FROM_MASK: the
+// lines are made on the fly from `data` and `flags` (no time-axis pass before this one), else
+// they are weight / out as the time-axis pass left them.  The results leave through the tile
+// they came in by, 4 r + 3 positions behind the reads, already normalised: out = filtered data /
+// filtered weight, NaN where that weight is 0 (twodflag.py:392-399); `weight` is not written.
+template <bool FROM_MASK>
+__device__ __noinline__ void box_freq_pass(const float *__restrict__ data, const uint8_t *__restrict__ flags,
+                                           const float *weight, float *out, int T, int F, int r)
+{
+    float *sm = s_sm;
+    const int tid = td_vtid(), lane = tid & 31, warp = tid >> 5, r2 = 2 * r;
+    const int lines = 2 * T;
+    int L = td_lines_that_fit(TD_SMEM_WORDS - 2 * TD_TILE_WORDS, 4 * r2, 32) & ~1;
+    if (L > lines) L = lines;
+    const int per_warp = 2 * TD_TILE_WORDS + 4 * r2 * L;
+    int conc = TD_SMEM_WORDS / per_warp;                 // warps that can work at the same time
+    if (conc > TD_WARPS) conc = TD_WARPS;
+    const float div = box_divisor(r);
+    const int len = F + 2 * r2, pitch = r2 * L, total = len + 3;
+    const int groups = (lines + L - 1) / L;
+    if (warp < conc) {
+        float *tiles = sm + warp * per_warp, *ring = tiles + 2 * TD_TILE_WORDS + lane;
+        for (int g = warp; g < groups; g += conc) {
+            const int first = g * L, nl = min(L, lines - first);
+            const bool active = lane < nl;
+            // request the tile of iterations step0 .. step0 + 31 (one commit group per tile)
+            auto request = [&](float *tile, int step0) {
+                const int idx = step0 + lane;
+                const bool inside = idx < F;
+                for (int ll = 0; ll < nl; ll++) {
+                    const int line = first + ll;
+                    const int64_t row = (int64_t) (line >> 1) * F;
+                    if (FROM_MASK) {
+                        float x = 0.0f;
+                        if (inside) {
+                            x = (line & 1) ? data[row + idx] : 1.0f;
+                            if (flags[row + idx]) x = 0.0f;
+                        }
+                        tile[ll * 33 + lane] = x;
+                    } else {
+                        const float *src = ((line & 1) ? out : weight) + row;
+                        cp_async4(tile + ll * 33 + lane, src + (inside ? idx : 0), inside);
+                    }
+                }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            };
+            if (active)
+                for (int s = 0; s < 4 * r2; s++) ring[s * L] = 0.0f;
+            BoxState<BoxF64> st = {0.0, 0.0, 0.0, 0.0, 0.0f, 0.0f, 0.0f};
+            int slot = 0, tb = 0;
+            request(tiles, 0);
+            for (int step0 = 0; step0 < total; step0 += 32, tb ^= 1) {
+                float *tile = tiles + tb * TD_TILE_WORDS;
+                if (step0 + 32 < total) {
+                    request(tiles + (tb ^ 1) * TD_TILE_WORDS, step0 + 32);
+                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                } else {
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                }
+                __syncwarp();
+                if (active) {
+                    const int kmax = min(32, total - step0);
+                    for (int k = 0; k < kmax; k++) {
+                        float o = 0.0f;
+                        const bool done = box_iter<BoxF64>(st, ring + slot * L, pitch, step0 + k, F, r2, tile[lane * 33 + k], o);
+                        tile[lane * 33 + k] = done ? __fdiv_rn(o, div) : 0.0f;
+                        slot = (slot + 1 == r2) ? 0 : slot + 1;
+                    }
+                }
+                __syncwarp();
+                const int oi = step0 + lane - 3 - 2 * r2;            // line position of what sits in column `lane`
+                if (oi >= 0 && oi < F) {
+                    for (int ll = 0; ll < nl; ll += 2) {
+                        const float w = tile[ll * 33 + lane], d = tile[(ll + 1) * 33 + lane];
+                        out[(int64_t) ((first + ll) >> 1) * F + oi] = (w == 0.0f) ? td_nan() : __fdiv_rn(d, w);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// ---- fallback for radii whose rings do not fit the shared memory: the reference's four passes
+// in place on a padded copy in global memory.  One line: n samples at data[k * stride], work
+// array padded[k * pstride] of n + 4 r floats.
+__device__ __noinline__ void box_line_in_place(const float *data, int64_t stride, float *padded, int64_t pstride, int n, int r,
+                                  float *out, int64_t ostride, float divisor)
+{
+    const int K = TD_PASSES;
+    const int padding = r * K, len = n + padding;
+    for (int i = 0; i < padding; i++) padded[(int64_t) i * pstride] = 0.0f;
+    for (int i = 0; i < n; i++) padded[(int64_t) (padding + i) * pstride] = data[(int64_t) i * stride];
+    for (int p = 1; p <= K; p++) {
+        double s = 0.0;
+        for (int i = 0; i < min(2 * r, len); i++) s = __dadd_rn(s, (double) padded[(int64_t) i * pstride]);
+        for (int i = 0; i < len; i++) {
+            if (i + 2 * r < len) s = __dadd_rn(s, (double) padded[(int64_t) (i + 2 * r) * pstride]);
+            const float prev = padded[(int64_t) i * pstride];
+            padded[(int64_t) i * pstride] = (float) s;
+            s = __dsub_rn(s, (double) prev);
+        }
+    }
+    for (int i = 0; i < n; i++) out[(int64_t) i * ostride] = __fdiv_rn(padded[(int64_t) i * pstride], divisor);
+}
+
+// twodflag.py:360-400: out = filtered (data with flagged samples zeroed) / filtered (weights),
+// NaN where the filtered weight is exactly 0.  Time axis first, then frequency
+// (twodflag.py:313-356).  The ring-based passes mask on the way in and normalise on the way out;
+// radii too large for the rings go through separate elementwise steps and the in-place lines.
+__device__ __noinline__ void masked_gaussian(const float *data, const uint8_t *flags, int T, int F, int r_t, int r_f,
+                                             float *out, float *weight)
+{
+    const int tid = threadIdx.x, A = T * F;
+    const bool time_ring = r_t > 0 && 8 * r_t <= TD_SMEM_WORDS;
+    const bool freq_ring = r_f > 0 && 8 * r_f <= TD_SMEM_WORDS - 2 * TD_TILE_WORDS;
+    const bool masked_first = time_ring || (r_t == 0 && freq_ring);
+    if (!masked_first) {
+        for (int i = tid; i < A; i += TD_THREADS) {
+            const bool fl = flags[i] != 0;
+            weight[i] = fl ? 0.0f : 1.0f;
+            out[i] = fl ? 0.0f : data[i];
+        }
+        __syncthreads();
+        td_mark(18);
+    }
+    float *pad = s_b.pad;
+    const int64_t pad_n = s_b.pad_n;
+    if (time_ring) {
+        box_time_pass(data, flags, weight, out, T, F, r_t);
+        td_mark(16);
+    } else if (r_t > 0) {
         const float div = box_divisor(r_t);
         for (int i = tid; i < 2 * F; i += TD_THREADS) {
             const int which = i >= F, f = which ? i - F : i;
-            float *arr = which ? arr1 : arr0;
-            box_line(arr + f, F, pad + which * pad_n + f, F, T, r_t, arr + f, F, div);
+            float *arr = which ? out : weight;
+            box_line_in_place(arr + f, F, pad + which * pad_n + f, F, T, r_t, arr + f, F, div);
         }
         __syncthreads();
+    }
+    if (freq_ring) {
+        if (r_t == 0) box_freq_pass<true>(data, flags, weight, out, T, F, r_f);
+        else box_freq_pass<false>(data, flags, weight, out, T, F, r_f);
+        td_mark(17);
+        return;
     }
     if (r_f > 0) {
         const float div = box_divisor(r_f);
         const int64_t plen = F + (int64_t) r_f * TD_PASSES;
         for (int i = tid; i < 2 * T; i += TD_THREADS) {
             const int which = i >= T, t = which ? i - T : i;
-            float *arr = which ? arr1 : arr0;
-            box_line(arr + (int64_t) t * F, 1, pad + which * pad_n + t * plen, 1, F, r_f, arr + (int64_t) t * F, 1, div);
+            float *arr = which ? out : weight;
+            box_line_in_place(arr + (int64_t) t * F, 1, pad + which * pad_n + t * plen, 1, F, r_f,
+                              arr + (int64_t) t * F, 1, div);
         }
         __syncthreads();
     }
-}
-
-// twodflag.py:360-400
-__device__ void masked_gaussian(const float *data, const uint8_t *flags, int T, int F, int r_t, int r_f,
-                                float *out, float *weight, float *pad, int64_t pad_n)
-{
-    const int tid = threadIdx.x, A = T * F;
     for (int i = tid; i < A; i += TD_THREADS) {
-        weight[i] = flags[i] ? 0.0f : 1.0f;
-        out[i] = flags[i] ? 0.0f : data[i];
+        const float w = weight[i];
+        out[i] = (w == 0.0f) ? td_nan() : __fdiv_rn(out[i], w);
     }
     __syncthreads();
-    box_filter_2d_pair(weight, out, T, F, r_t, r_f, pad, pad_n);
-    for (int i = tid; i < A; i += TD_THREADS)
-        out[i] = (weight[i] == 0.0f) ? __int_as_float(0x7fc00000) : __fdiv_rn(out[i], weight[i]);
-    __syncthreads();
+    td_mark(18);
 }
 
-// twodflag.py:200-251, one row
-__device__ void interpolate_row(float *row, int n)
+// twodflag.py:200-251, one row by one warp.  NaN runs are filled from the values on both sides
+// (linearly, in float64), or with the nearest value at the ends of the row, or with zeros if the
+// row holds nothing else.  `next_valid` (one int per element) is scratch.
+__device__ __noinline__ void interpolate_row(float *row, int *next_valid, int n, int lane)
 {
-    int p = 0;
-    while (p < n && isnan(row[p])) p++;
-    if (p == n) {
-        for (int i = 0; i < n; i++) row[i] = 0.0f;
-        return;
+    // backward sweep: for every element the position of the first valid one at or after it
+    int carry = n;
+    bool any_nan = false;
+    for (int base = ((n - 1) / 32) * 32; base >= 0; base -= 32) {
+        const int i = base + lane;
+        const bool valid = i < n && !isnan(row[i]);
+        const uint32_t m = __ballot_sync(FULL, valid);
+        if (__popc(m) != min(32, n - base)) any_nan = true;
+        const uint32_t at_or_after = m & (FULL << lane);
+        if (i < n) next_valid[i] = at_or_after ? base + __ffs(at_or_after) - 1 : carry;
+        if (m) carry = base + __ffs(m) - 1;
     }
-    for (int i = 0; i < p; i++) row[i] = row[p];
-    p++;
-    while (p < n) {
-        if (isnan(row[p])) {
-            int q = p + 1;
-            while (q < n && isnan(row[q])) q++;
-            if (q == n) {
-                for (int i = p; i < n; i++) row[i] = row[p - 1];
+    if (!any_nan) return;                                          // warp-uniform
+    __syncwarp();
+    // forward sweep: the last valid position before each NaN, then the fill (valid elements never change)
+    int prev_i = -1;
+    float prev_v = 0.0f;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        const float v = i < n ? row[i] : 0.0f;
+        const bool valid = i < n && !isnan(v);
+        const uint32_t m = __ballot_sync(FULL, valid);
+        const uint32_t before = m & ((1u << lane) - 1u);
+        const int src = before ? 31 - __clz(before) : 0;
+        const float tv = __shfl_sync(FULL, v, src);
+        const int p = before ? base + src : prev_i;
+        const float pv = before ? tv : prev_v;
+        const int last_src = m ? 31 - __clz(m) : 0;
+        const float lv = __shfl_sync(FULL, v, last_src);
+        if (i < n && !valid) {
+            const int q = next_valid[i];
+            float fill;
+            if (p < 0 && q >= n) {
+                fill = 0.0f;
+            } else if (p < 0) {
+                fill = row[q];
+            } else if (q >= n) {
+                fill = pv;
             } else {
-                const float start = row[p - 1];
-                const double grad = (double) __fsub_rn(row[q], start) / (double) (q - (p - 1));
-                for (int i = p; i < q; i++)
-                    row[i] = (float) __dadd_rn((double) start, __dmul_rn((double) (i - (p - 1)), grad));
+                const double grad = __ddiv_rn((double) __fsub_rn(row[q], pv), (double) (q - p));
+                fill = (float) __dadd_rn((double) pv, __dmul_rn((double) (i - p), grad));
             }
-            p = q;
-        } else {
-            p++;
+            row[i] = fill;
+        }
+        if (m) {
+            prev_i = base + last_src;
+            prev_v = lv;
         }
     }
 }
 
 // twodflag.py:404-463.  flags_in is not modified; `work` receives the growing mask.
-__device__ void background2d(const TdArgs &a, const float *data, const uint8_t *flags_in, int T, int F,
-                             const int *r_t, const int *r_f, float *bg, uint8_t *work, float *weight,
-                             float *pad, int64_t pad_n, const SelectScratch &sc, uint32_t *s_count)
+// spectrum: the 1 x F median spectrum (no time axis) instead of the T x F array.
+__device__ __noinline__ void background2d(bool spectrum, int ph)
 {
-    const int tid = threadIdx.x, A = T * F;
+    const TdArgs &a = s_a;
+    const int tid = td_vtid(), lane = tid & 31, warp = tid >> 5;
+    const int T = spectrum ? 1 : (int) a.p.n_time, F = a.a_freq, A = T * F;
+    const float *data = spectrum ? s_b.spec_data : s_b.data;
+    const uint8_t *flags_in = spectrum ? s_b.spec_flags : s_b.flags;
+    float *bg = spectrum ? s_b.spec_bg : s_b.bg;
+    float *weight = spectrum ? s_b.spec_weight : s_b.weight;
+    uint8_t *work = spectrum ? s_b.spec_work : s_b.work;
     for (int i = tid; i < A; i += TD_THREADS) work[i] = flags_in[i] != 0;
     __syncthreads();
     for (int ef = a.p.background_iterations; ef >= 1; ef--) {
-        masked_gaussian(data, work, T, F, r_t ? r_t[ef] : 0, r_f[ef], bg, weight, pad, pad_n);
-        for (int c = 0; c < a.p.n_chunks; c++) {
-            const int c0 = (int) a.p.chunk_ends[c], c1 = (int) a.p.chunk_ends[c + 1], cl = c1 - c0;
-            for (int i = tid; i < T * cl; i += TD_THREADS) {
-                const int o = (i / cl) * F + c0 + i % cl;
-                bg[o] = fabsf(__fsub_rn(data[o], bg[o]));
-            }
-            __syncthreads();
+        masked_gaussian(data, work, T, F, spectrum ? 0 : a.p.r_time[ef], a.p.r_freq[ef], bg, weight);
+        td_mark(ph);
+        // per chunk (they are disjoint sets of columns): |residual|, its median over the samples
+        // still unflagged, rejection above background_reject sigma.  One warp per chunk.
+        for (int c = warp; c < a.p.n_chunks; c += TD_WARPS) {
+            const int c0 = (int) a.p.chunk_ends[c], cl = (int) a.p.chunk_ends[c + 1] - c0;
+            if (cl <= 0) continue;
+            for (int t = 0; t < T; t++)
+                for (int j = lane; j < cl; j += 32) {
+                    const int o = t * F + c0 + j;
+                    bg[o] = fabsf(__fsub_rn(data[o], bg[o]));
+                }
+            __syncwarp();
+            const int rows32 = (cl + 31) / 32 * 32;                  // whole warps per row: coalesced
             auto key_at = [=](int i) -> uint32_t {
-                const int o = (i / cl) * F + c0 + i % cl;
-                return work[o] ? KEY_SKIP : __float_as_uint(bg[o]);       // residuals are >= 0
+                const int t = i / rows32, j = i - t * rows32;
+                if (j >= cl) return KEY_SKIP;
+                const int o = t * F + c0 + j;
+                return work[o] ? KEY_SKIP : __float_as_uint(bg[o]);   // residuals are >= 0
             };
-            const float med = block_median_abs(key_at, T * cl, sc, s_count);
+            const float med = warp_median(key_at, T * rows32, s_whist + warp * 256, lane);
             const double threshold = __dmul_rn((double) med, __dmul_rn(TD_MAD_NORMAL, a.p.background_reject));
-            for (int i = tid; i < T * cl; i += TD_THREADS) {
-                const int o = (i / cl) * F + c0 + i % cl;
-                if ((double) bg[o] > threshold) work[o] = 1;
-            }
-            __syncthreads();
+            for (int t = 0; t < T; t++)
+                for (int j = lane; j < cl; j += 32) {
+                    const int o = t * F + c0 + j;
+                    if ((double) bg[o] > threshold) work[o] = 1;
+                }
         }
+        __syncthreads();
+        td_mark(ph + 1);
     }
-    masked_gaussian(data, work, T, F, r_t ? r_t[1] : 0, r_f[1], bg, weight, pad, pad_n);
-    for (int t = tid; t < T; t += TD_THREADS) interpolate_row(bg + (int64_t) t * F, F);
+    masked_gaussian(data, work, T, F, spectrum ? 0 : a.p.r_time[1], a.p.r_freq[1], bg, weight);
+    td_mark(ph);
+    for (int t = warp; t < T; t += TD_WARPS)
+        interpolate_row(bg + (int64_t) t * F, reinterpret_cast<int *>(weight) + (int64_t) t * F, F, lane);
     __syncthreads();
+    td_mark(ph + 2);
 }
 
 // ------------------------------------------------------------------ SumThreshold, one line (twodflag.py:493-560)
-// A chunk of `clen` samples starting `coff` samples into its padded slice of `len` samples
-// (the chunk extended by the largest window - 1 on both sides, clipped to the array):
-// line[i * stride], i < len.  thr32 = the chunk's threshold (already scaled; inf without data).
-// pos / neg / hp / hn: work bytes, [i * wstride].  Writes out[k * ostride], k < clen.
-__device__ void sum_threshold_line(const float *line, int64_t stride, int len, int coff, int clen, float thr32,
-                                   const int *windows, int n_windows, const double *tf, uint8_t *pos,
-                                   uint8_t *neg, uint8_t *hp, uint8_t *hn, int64_t wstride, uint8_t *out,
-                                   int64_t ostride)
+// The reference, per window size w (in order): lim = thr / tf; samples already flagged (positive
+// or negative side) are clamped to +-lim; cum = running float64 sum; window k .. k + w - 1 is a
+// hit if (cum[k + w] - cum[k]) * float32(1 / w) > lim (positive side; the negative side with
+// -scale); after the sweep every hit flags the w samples of its window.  Here: one sweep per
+// window size with the last w + 1 cumulative sums in a ring (ring[slot * L]); sample k is flagged
+// exactly if one of the windows k - w + 1 .. k fired, i.e. if any of the last w hits is set when
+// hit k has been shifted in - so the flag of sample k is final w - 1 steps after it was read, and
+// reads of the masks (32 samples at a time) always see the state before this window size.
+// x(i), i < len: the line.  posw / negw: the line's bit masks, word j at [j * wpitch].
+template <typename LineAt>
+__device__ void sum_threshold_line(const LineAt &x_at, int len, float thr32, const int *windows, int n_windows,
+                                   const double *tf, uint32_t *posw, uint32_t *negw, int64_t wpitch, double *ring,
+                                   int L)
 {
-    for (int i = 0; i < len; i++) pos[i * wstride] = neg[i * wstride] = 0;
+    const int nw = (len + 31) >> 5;
+    for (int j = 0; j < nw; j++) posw[j * wpitch] = negw[j * wpitch] = 0u;
     for (int wi = 0; wi < n_windows; wi++) {
         const int w = windows[wi];
-        const float lim = (float) ((double) thr32 / tf[wi]);
-        const double scale = (double) (float) (1.0 / (double) w);       // np.float32(1.0 / window)
+        const float lim = (float) __ddiv_rn((double) thr32, tf[wi]);
+        const float nlim = -lim;
+        const double scale = (double) (float) __ddiv_rn(1.0, (double) w);       // np.float32(1.0 / window)
+        const double nscale = -scale;
         const double dlim = (double) lim;
-        double ring[KSP_TWOD_MAX_WINDOW + 1];                           // cum[j] at j mod (w + 1)
+        const unsigned long long keep = w >= 64 ? ~0ull : ((1ull << w) - 1ull);
+        unsigned long long hits_p = 0ull, hits_n = 0ull;
         double cum = 0.0;
+        int head = 0;
         ring[0] = 0.0;
-        for (int i = 0; i < len; i++) {
-            float x = line[i * stride];
-            if (pos[i * wstride] && x > lim) x = lim;
-            else if (neg[i * wstride] && x < -lim) x = -lim;
-            cum += (double) x;
-            ring[(i + 1) % (w + 1)] = cum;
-            hp[i * wstride] = hn[i * wstride] = 0;
-            if (i + 1 >= w) {
-                const int k = i + 1 - w;                                 // the window k .. k + w - 1
-                const double avg = cum - ring[k % (w + 1)];
-                hp[k * wstride] = (avg * scale) > dlim;
-                hn[k * wstride] = (avg * -scale) > dlim;
+        uint32_t rp = 0u, rn = 0u, wp = 0u, wn = 0u;
+        const int total = len + w - 1;
+        for (int i0 = 0; i0 < total; i0 += 4) {
+            float xs[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) xs[u] = (i0 + u < len) ? x_at(i0 + u) : 0.0f;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int i = i0 + u;
+                if (i >= total) break;
+                const bool inside = i < len;
+                if (inside) {
+                    if ((i & 31) == 0) {
+                        rp = posw[(i >> 5) * wpitch];
+                        rn = negw[(i >> 5) * wpitch];
+                    }
+                    const uint32_t bit = 1u << (i & 31);
+                    float x = xs[u];
+                    if ((rp & bit) && x > lim) x = lim;
+                    else if ((rn & bit) && x < nlim) x = nlim;
+                    cum = __dadd_rn(cum, (double) x);
+                    head = (head == w) ? 0 : head + 1;
+                    ring[head * L] = cum;
+                }
+                const int k = i + 1 - w;
+                if (k >= 0) {
+                    unsigned long long hp = 0ull, hn = 0ull;
+                    if (inside) {
+                        const int oldest = (head == w) ? 0 : head + 1;
+                        const double sum = __dsub_rn(cum, ring[oldest * L]);
+                        hp = __dmul_rn(sum, scale) > dlim;
+                        hn = __dmul_rn(sum, nscale) > dlim;
+                    }
+                    hits_p = ((hits_p << 1) | hp) & keep;
+                    hits_n = ((hits_n << 1) | hn) & keep;
+                    wp |= (hits_p != 0ull ? 1u : 0u) << (k & 31);
+                    wn |= (hits_n != 0ull ? 1u : 0u) << (k & 31);
+                    if ((k & 31) == 31 || k == len - 1) {
+                        if (wp) posw[(k >> 5) * wpitch] |= wp;
+                        if (wn) negw[(k >> 5) * wpitch] |= wn;
+                        wp = wn = 0u;
+                    }
+                }
             }
         }
-        // every hit flags the samples of its window
-        int run_p = 0, run_n = 0;
-        for (int i = 0; i < len; i++) {
-            if (hp[i * wstride]) run_p = w;
-            if (hn[i * wstride]) run_n = w;
-            if (run_p > 0) { pos[i * wstride] = 1; run_p--; }
-            if (run_n > 0) { neg[i * wstride] = 1; run_n--; }
-        }
     }
-    for (int k = 0; k < clen; k++) out[k * ostride] = pos[(coff + k) * wstride] | neg[(coff + k) * wstride];
 }
 
 __device__ __forceinline__ float scaled_threshold(float med, double outlier_nsigma)
@@ -413,172 +974,256 @@ __device__ __forceinline__ float scaled_threshold(float med, double outlier_nsig
     return (float) __dmul_rn((double) med, __dmul_rn(outlier_nsigma, TD_MAD_NORMAL));
 }
 
-// SumThreshold along frequency with per-chunk thresholds (axis 1): T rows x n_chunks chunks,
-// one thread per (row, chunk), each with its own work slice.
-__device__ void sum_threshold_freq(const TdArgs &a, const float *data, const uint8_t *flags, int T, int F,
-                                   uint8_t *out, const TdBuffers &b, const SelectScratch &sc, uint32_t *s_count)
+// SumThreshold along frequency with per-chunk thresholds (axis 1): T rows x n_chunks chunks.
+// Thresholds: one warp per (row, chunk).  Lines: one thread per (row, chunk) over the chunk
+// extended by the largest window - 1 on both sides (clipped to the row); the flags of the chunk
+// itself are then written out by one warp per line.
+__device__ __noinline__ void sum_threshold_freq(bool spectrum, int ph)
 {
-    const int tid = threadIdx.x;
-    const int nc = a.p.n_chunks;
-    const int max_w = a.max_wf;
-    // thresholds: median of |data| over the unflagged samples of (row, chunk), the whole block at a time
-    for (int t = 0; t < T; t++)
-        for (int c = 0; c < nc; c++) {
-            const int c0 = (int) a.p.chunk_ends[c], cl = (int) a.p.chunk_ends[c + 1] - c0;
-            const float *row = data + (int64_t) t * F + c0;
-            const uint8_t *frow = flags + (int64_t) t * F + c0;
-            auto key_at = [=](int i) -> uint32_t {
-                return frow[i] ? KEY_SKIP : (__float_as_uint(row[i]) & 0x7fffffffu);
-            };
-            const float med = block_median_abs(key_at, cl, sc, s_count);
-            if (tid == 0) b.thr[t * nc + c] = scaled_threshold(med, a.p.outlier_nsigma);
-        }
+    const TdArgs &a = s_a;
+    const TdBuffers &b = s_b;
+    const int tid = td_vtid(), lane = tid & 31, warp = tid >> 5;
+    const int T = spectrum ? 1 : (int) a.p.n_time, F = a.a_freq;
+    const float *data = spectrum ? b.spec_data : b.data;
+    const uint8_t *flags = spectrum ? b.spec_flags : b.flags;
+    uint8_t *out = spectrum ? b.spec_out : b.ffl;
+    const int nc = a.p.n_chunks, max_w = a.max_wf, lines = T * nc;
+    for (int i = warp; i < lines; i += TD_WARPS) {
+        const int t = i / nc, c = i - t * nc;
+        const int c0 = (int) a.p.chunk_ends[c], cl = (int) a.p.chunk_ends[c + 1] - c0;
+        const float *row = data + (int64_t) t * F + c0;
+        const uint8_t *frow = flags + (int64_t) t * F + c0;
+        auto key_at = [=](int j) -> uint32_t {
+            return frow[j] ? KEY_SKIP : (__float_as_uint(row[j]) & 0x7fffffffu);
+        };
+        const float med = warp_median(key_at, cl, s_whist + warp * 256, lane);
+        if (lane == 0) b.thr[i] = scaled_threshold(med, a.p.outlier_nsigma);
+    }
     __syncthreads();
-    const int64_t row_work = (int64_t) td_row_work(a.p, F, max_w);
-    for (int i = tid; i < T * nc; i += TD_THREADS) {
-        const int t = i / nc, c = i % nc;
+    td_mark(ph);
+    double *ring = reinterpret_cast<double *>(s_sm);
+    const int L = td_lines_that_fit(TD_SMEM_WORDS / 2, max_w + 1, TD_THREADS);
+    for (int base = 0; base < lines; base += L) {
+        const int i = base + tid;
+        if (tid < L && i < lines) {
+            const int t = i / nc, c = i - t * nc;
+            const int c0 = (int) a.p.chunk_ends[c], c1 = (int) a.p.chunk_ends[c + 1];
+            if (c1 > c0) {
+                const int p0 = max(c0 - max_w + 1, 0), p1 = min(c1 + max_w - 1, F);
+                const float *line = data + (int64_t) t * F + p0;
+                auto x_at = [=](int j) -> float { return line[j]; };
+                sum_threshold_line(x_at, p1 - p0, b.thr[i], a.p.windows_freq, a.p.n_windows_freq, a.p.tf_freq,
+                                   b.posw + i, b.negw + i, lines, ring + tid, L);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = warp; i < lines; i += TD_WARPS) {
+        const int t = i / nc, c = i - t * nc;
         const int c0 = (int) a.p.chunk_ends[c], c1 = (int) a.p.chunk_ends[c + 1];
-        if (c1 <= c0) continue;
-        const int p0 = max(c0 - max_w + 1, 0), p1 = min(c1 + max_w - 1, F);
-        const int64_t wo = (int64_t) t * row_work + c0 + (int64_t) c * 2 * max_w;   // slices never overlap
-        sum_threshold_line(data + (int64_t) t * F + p0, 1, p1 - p0, c0 - p0, c1 - c0, b.thr[t * nc + c],
-                           a.p.windows_freq, a.p.n_windows_freq, a.p.tf_freq, b.pos + wo, b.neg + wo,
-                           b.hp + wo, b.hn + wo, 1, out + (int64_t) t * F + c0, 1);
+        const int coff = c0 - max(c0 - max_w + 1, 0);
+        for (int j = lane; j < c1 - c0; j += 32) {
+            const int bitpos = coff + j;
+            const uint32_t m = b.posw[(int64_t) (bitpos >> 5) * lines + i] | b.negw[(int64_t) (bitpos >> 5) * lines + i];
+            out[(int64_t) t * F + c0 + j] = (m >> (bitpos & 31)) & 1u;
+        }
+    }
+    __syncthreads();
+    td_mark(ph + 1);
+}
+
+// Median over time of every column's unflagged samples (twodflag.py:120-158)
+__device__ __noinline__ void median_spectrum()
+{
+    const TdBuffers &b = s_b;
+    const int T = (int) s_a.p.n_time, F = s_a.a_freq;
+    for (int f = threadIdx.x; f < F; f += TD_THREADS) {
+        int n;
+        const float med = column_median_any<false>(b.data + f, b.flags + f, b.vals + f, F, T, &n);
+        b.spec_data[f] = n ? med : 0.0f;
+        b.spec_flags[f] = n == 0;
     }
     __syncthreads();
 }
 
-// ------------------------------------------------------------------ one baseline (twodflag.py:768-881)
-__global__ void __launch_bounds__(TD_THREADS, 4)
-twod_baseline_kernel(const TdArgs a)
+// SumThreshold along time: one column per thread, one chunk [0, T)
+__device__ __noinline__ void sum_threshold_time()
 {
-    __shared__ uint32_t s_hist[SELECT_HIST_WORDS];
-    __shared__ uint32_t s_misc[64];
-    __shared__ uint32_t s_count;
-    SelectScratch sc;
-    sc.hist = s_hist;
-    sc.misc = s_misc;
-    const int tid = threadIdx.x;
-    const int T = (int) a.p.n_time, F = a.a_freq, A = T * F;
-    for (int64_t blr = blockIdx.x; blr < a.nb; blr += gridDim.x) {
-        TdBuffers b;
-        td_buffers(a, blr, &b);
-
-        // ---- median spectrum over time (twodflag.py:120-158)
-        for (int f = tid; f < F; f += TD_THREADS) {
-            float *v = b.vals + (int64_t) f * T;
-            int n = 0;
-            for (int t = 0; t < T; t++)
-                if (!b.flags[(int64_t) t * F + f]) v[n++] = b.data[(int64_t) t * F + f];
-            if (n == 0) {
-                b.spec_data[f] = 0.0f;
-                b.spec_flags[f] = 1;
-            } else {
-                sort_small(v, n);
-                b.spec_data[f] = median_sorted_f32(v, n);
-                b.spec_flags[f] = 0;
-            }
-        }
-        __syncthreads();
-        // ---- background and SumThreshold of the spectrum
-        background2d(a, b.spec_data, b.spec_flags, 1, F, nullptr, a.p.r_freq, b.spec_bg, b.spec_work,
-                     b.spec_weight, b.pad, b.pad_n, sc, &s_count);
-        for (int f = tid; f < F; f += TD_THREADS) b.spec_data[f] = __fsub_rn(b.spec_data[f], b.spec_bg[f]);
-        __syncthreads();
-        sum_threshold_freq(a, b.spec_data, b.spec_flags, 1, F, b.spec_out, b, sc, &s_count);
-        for (int i = tid; i < A; i += TD_THREADS) b.flags[i] |= b.spec_out[i % F];
-        __syncthreads();
-        // ---- 2-D background
-        background2d(a, b.data, b.flags, T, F, a.p.r_time, a.p.r_freq, b.bg, b.work, b.weight, b.pad, b.pad_n, sc, &s_count);
-        for (int i = tid; i < A; i += TD_THREADS) b.data[i] = __fsub_rn(b.data[i], b.bg[i]);
-        __syncthreads();
-        // ---- SumThreshold along time: one column per thread, one chunk [0, T)
-        for (int f = tid; f < F; f += TD_THREADS) {
-            float *v = b.vals + (int64_t) f * T;
-            int n = 0;
-            for (int t = 0; t < T; t++)
-                if (!b.flags[(int64_t) t * F + f]) v[n++] = fabsf(b.data[(int64_t) t * F + f]);
-            float med = __int_as_float(0x7fc00000);
-            if (n > 0) {
-                sort_small(v, n);
-                med = median_sorted_f32(v, n);
-            }
-            sum_threshold_line(b.data + f, F, T, 0, T, scaled_threshold(med, a.p.outlier_nsigma),
-                               a.p.windows_time, a.p.n_windows_time, a.p.tf_time, b.pos + f, b.neg + f,
-                               b.hp + f, b.hn + f, F, b.tfl + f, F);
-        }
-        __syncthreads();
-        for (int i = tid; i < A; i += TD_THREADS) b.flags[i] |= b.tfl[i];
-        __syncthreads();
-        // ---- SumThreshold along frequency
-        sum_threshold_freq(a, b.data, b.flags, T, F, b.ffl, b, sc, &s_count);
-        // ---- combine and smear in time (twodflag.py:691-722)
-        {
-            const int lo = -(a.p.time_extend / 2), hi = lo + a.p.time_extend;
-            for (int f = tid; f < F; f += TD_THREADS) {
-                // any flag in rows [t + lo, t + hi) clipped to the array
-                for (int t = 0; t < T; t++) {
-                    const int t0 = max(t + lo, 0), t1 = min(t + hi, T);
-                    uint8_t any = 0;
-                    for (int k = t0; k < t1; k++)
-                        any |= b.spec_out[f] | b.tfl[(int64_t) k * F + f] | b.ffl[(int64_t) k * F + f];
-                    b.comb[(int64_t) t * F + f] = any;
+    const TdArgs &a = s_a;
+    const TdBuffers &b = s_b;
+    const int tid = td_vtid();
+    const int T = (int) a.p.n_time, F = a.a_freq;
+    double *ring = reinterpret_cast<double *>(s_sm);
+    const int L = td_lines_that_fit(TD_SMEM_WORDS / 2, a.max_wt + 1, TD_THREADS);
+    const int words = (T + 31) >> 5;
+    for (int base = 0; base < F; base += L) {
+        const int f = base + tid;
+        if (tid < L && f < F) {
+            int n;
+            const float med = column_median_any<true>(b.data + f, b.flags + f, b.vals + f, F, T, &n);
+            const float *col = b.data + f;
+            const int64_t stride = F;
+            auto x_at = [=](int j) -> float { return col[(int64_t) j * stride]; };
+            sum_threshold_line(x_at, T, scaled_threshold(med, a.p.outlier_nsigma), a.p.windows_time,
+                               a.p.n_windows_time, a.p.tf_time, b.posw + f, b.negw + f, F, ring + tid, L);
+            for (int j = 0; j < words; j++) {
+                const uint32_t m = b.posw[(int64_t) j * F + f] | b.negw[(int64_t) j * F + f];
+                for (int t = j * 32; t < min(T, j * 32 + 32); t++) {
+                    const uint8_t fl = (m >> (t & 31)) & 1u;
+                    b.tfl[(int64_t) t * F + f] = fl;
+                    b.flags[(int64_t) t * F + f] |= fl;
                 }
             }
         }
-        __syncthreads();
-        // ---- back to the original channels, smear in frequency, fill rows / columns (twodflag.py:726-764)
-        {
-            const int OF = (int) a.p.n_freq, avg = a.p.average_freq;
-            const int lo = -(a.p.freq_extend / 2), hi = lo + a.p.freq_extend;
-            for (int i = tid; i < T * OF; i += TD_THREADS) {
-                const int t = i / OF, f = i % OF;
-                const int f0 = max(f + lo, 0), f1 = min(f + hi, OF);
+    }
+    __syncthreads();
+}
+
+// Combination of the three flag sets, smearing in time; back to the original channels, smearing
+// in frequency, fill rules (twodflag.py:691-764)
+__device__ __noinline__ void combine_and_unaverage()
+{
+    const TdArgs &a = s_a;
+    const TdBuffers &b = s_b;
+    const int tid = td_vtid(), lane = tid & 31, warp = tid >> 5;
+    const int T = (int) a.p.n_time, F = a.a_freq;
+    {
+        const int lo = -(a.p.time_extend / 2), hi = lo + a.p.time_extend;
+        for (int f = tid; f < F; f += TD_THREADS) {
+            // any flag in rows [t + lo, t + hi) clipped to the array
+            const uint8_t spec = b.spec_out[f];
+            for (int t = 0; t < T; t++) {
+                const int t0 = max(t + lo, 0), t1 = min(t + hi, T);
                 uint8_t any = 0;
-                for (int k = f0; k < f1; k++) any |= b.comb[(int64_t) t * F + k / avg];
-                b.outb[i] = any;
+                for (int k = t0; k < t1; k++)
+                    any |= spec | b.tfl[(int64_t) k * F + f] | b.ffl[(int64_t) k * F + f];
+                b.comb[(int64_t) t * F + f] = any;
             }
-            __syncthreads();
-            // rows with too many flags (counted before any filling), then columns likewise
-            uint8_t *row_full = b.row_full, *col_full = b.col_full;
-            for (int t = tid; t < T; t += TD_THREADS) {
-                int tot = 0;
-                for (int f = 0; f < OF; f++) tot += b.outb[(int64_t) t * OF + f];
-                row_full[t] = (double) tot > a.p.flag_all_freq_frac * (double) OF;
-            }
-            for (int f = tid; f < OF; f += TD_THREADS) {
-                int tot = 0;
-                for (int t = 0; t < T; t++) tot += b.outb[(int64_t) t * OF + f];
-                col_full[f] = (double) tot > (double) T * a.p.flag_all_time_frac;
-            }
-            __syncthreads();
-            for (int i = tid; i < T * OF; i += TD_THREADS)
-                if (row_full[i / OF] || col_full[i % OF]) b.outb[i] = 1;
-            __syncthreads();
         }
+    }
+    __syncthreads();
+    td_mark(12);
+    const int OF = (int) a.p.n_freq, avg = a.p.average_freq;
+    const int lo = -(a.p.freq_extend / 2), hi = lo + a.p.freq_extend;
+    for (int t = 0; t < T; t++) {
+        const uint8_t *crow = b.comb + (int64_t) t * F;
+        for (int f = tid; f < OF; f += TD_THREADS) {
+            const int f0 = max(f + lo, 0), f1 = min(f + hi, OF);
+            uint8_t any = 0;
+            if (avg == 1)
+                for (int k = f0; k < f1; k++) any |= crow[k];
+            else
+                for (int k = f0; k < f1; k++) any |= crow[k / avg];
+            b.outb[(int64_t) t * OF + f] = any;
+        }
+    }
+    __syncthreads();
+    // rows with too many flags (counted before any filling), then columns likewise
+    uint8_t *row_full = b.row_full, *col_full = b.col_full;
+    for (int t = warp; t < T; t += TD_WARPS) {
+        int tot = 0;
+        for (int f = lane; f < OF; f += 32) tot += b.outb[(int64_t) t * OF + f];
+        tot = __reduce_add_sync(FULL, tot);
+        if (lane == 0) row_full[t] = (double) tot > a.p.flag_all_freq_frac * (double) OF;
+    }
+    for (int f = tid; f < OF; f += TD_THREADS) {
+        int tot = 0;
+        for (int t = 0; t < T; t++) tot += b.outb[(int64_t) t * OF + f];
+        col_full[f] = (double) tot > (double) T * a.p.flag_all_time_frac;
+    }
+    __syncthreads();
+    for (int t = 0; t < T; t++) {
+        const bool rf = row_full[t] != 0;
+        for (int f = tid; f < OF; f += TD_THREADS)
+            if (rf || col_full[f]) b.outb[(int64_t) t * OF + f] = 1;
+    }
+    __syncthreads();
+    td_mark(13);
+}
+
+// ------------------------------------------------------------------ one baseline (twodflag.py:768-881)
+__global__ void __launch_bounds__(TD_THREADS, TD_BLOCKS_PER_SM)
+twod_baseline_kernel(const TdArgs a)
+{
+    const int tid = threadIdx.x;
+    {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&a);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(&s_a);
+        for (int i = tid; i < (int) (sizeof(TdArgs) / 4); i += TD_THREADS) dst[i] = src[i];
+    }
+    const int T = (int) a.p.n_time, F = a.a_freq, A = T * F;
+    for (int64_t blr = blockIdx.x; blr < a.nb; blr += gridDim.x) {
+        __syncthreads();
+        if (tid == 0) {
+            td_buffers(a, blr, &s_b);
+            s_last = clock64();
+        }
+        __syncthreads();
+        const TdBuffers &b = s_b;
+        median_spectrum();
+        td_mark(0);
+        // ---- background and SumThreshold of the spectrum
+        background2d(true, 1);
+        for (int f = tid; f < F; f += TD_THREADS) b.spec_data[f] = __fsub_rn(b.spec_data[f], b.spec_bg[f]);
+        __syncthreads();
+        sum_threshold_freq(true, 4);
+        for (int t = 0; t < T; t++)
+            for (int f = tid; f < F; f += TD_THREADS) b.flags[(int64_t) t * F + f] |= b.spec_out[f];
+        __syncthreads();
+        td_mark(15);
+        // ---- 2-D background
+        background2d(false, 6);
+        for (int i = tid; i < A; i += TD_THREADS) b.data[i] = __fsub_rn(b.data[i], b.bg[i]);
+        __syncthreads();
+        td_mark(15);
+        sum_threshold_time();
+        td_mark(9);
+        sum_threshold_freq(false, 10);
+        combine_and_unaverage();
     }
 }
 
 // ------------------------------------------------------------------ output (twodflag.py:680-688)
+// Block = 32 baselines x 32 channels of one dump, transposed through shared memory.
 template <bool COMPLEX>
 __global__ void __launch_bounds__(256)
 twod_output_kernel(const TdArgs a)
 {
-    const int64_t total = a.nb * a.p.n_time * a.p.n_freq;
-    const int64_t i = (int64_t) blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    const int64_t blr = i % a.nb, rest = i / a.nb;             // rest = t * n_freq + f
-    TdBuffers b;
-    td_buffers(a, blr, &b);
-    const int64_t idx = rest * a.p.n_bl + a.bl0 + blr;
-    bool nan_in;
-    if (COMPLEX) {
-        const float2 v = reinterpret_cast<const float2 *>(a.data)[idx];
-        nan_in = isnan(v.x) || isnan(v.y);
-    } else {
-        nan_in = isnan(reinterpret_cast<const float *>(a.data)[idx]);
+    __shared__ uint8_t s_flag[32][33];
+    const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    const int64_t bl_tile = (int64_t) blockIdx.x * 32;
+    const int f_tile = (int) blockIdx.y * 32;
+    const int t = (int) blockIdx.z;
+    const int OF = (int) a.p.n_freq;
+    {
+        const int f = f_tile + lane;
+        for (int bo = wrp; bo < 32; bo += 8) {
+            const int64_t bl = bl_tile + bo;
+            uint8_t v = 0;
+            if (bl < a.nb && f < OF) {
+                TdBuffers b;
+                td_buffers(a, bl, &b);
+                v = b.outb[(int64_t) t * OF + f];
+            }
+            s_flag[bo][lane] = v;
+        }
     }
-    a.out_flags[idx] = (b.outb[rest] || nan_in) ? 1 : 0;
+    __syncthreads();
+    const int64_t blr = bl_tile + lane;
+    for (int fo = wrp; fo < 32; fo += 8) {
+        const int f = f_tile + fo;
+        if (blr < a.nb && f < OF) {
+            const int64_t idx = ((int64_t) t * OF + f) * a.p.n_bl + a.bl0 + blr;
+            bool nan_in;
+            if (COMPLEX) {
+                const float2 v = __ldg(reinterpret_cast<const float2 *>(a.data) + idx);
+                nan_in = isnan(v.x) || isnan(v.y);
+            } else {
+                nan_in = isnan(__ldg(reinterpret_cast<const float *>(a.data) + idx));
+            }
+            a.out_flags[idx] = (s_flag[lane][fo] || nan_in) ? 1 : 0;
+        }
+    }
 }
 
 void fill_derived(TdArgs &a)
@@ -589,17 +1234,25 @@ void fill_derived(TdArgs &a)
         if (a.p.r_time[e] > a.max_rt) a.max_rt = a.p.r_time[e];
         if (a.p.r_freq[e] > a.max_rf) a.max_rf = a.p.r_freq[e];
     }
-    a.max_wf = 1;
+    a.max_wf = a.max_wt = 1;
     for (int i = 0; i < a.p.n_windows_freq; i++)
         if (a.p.windows_freq[i] > a.max_wf) a.max_wf = a.p.windows_freq[i];
-    a.per_bl = td_layout(a.p, a.a_freq, a.max_rt, a.max_rf, a.max_wf, nullptr, nullptr);
+    for (int i = 0; i < a.p.n_windows_time; i++)
+        if (a.p.windows_time[i] > a.max_wt) a.max_wt = a.p.windows_time[i];
+    a.max_cl = 0;
+    for (int c = 0; c < a.p.n_chunks; c++) {
+        const int cl = (int) (a.p.chunk_ends[c + 1] - a.p.chunk_ends[c]);
+        if (cl > a.max_cl) a.max_cl = cl;
+    }
+    a.big_radius = 8 * a.max_rt > TD_SMEM_WORDS || 8 * a.max_rf > TD_SMEM_WORDS - 2 * TD_TILE_WORDS;
+    a.per_bl = td_layout(a, nullptr, nullptr);
 }
 
 int check_params(const ksp_twodflag_params *p)
 {
     if (!p) return KSP_EINVAL;
     if (p->n_time < 1 || p->n_freq < 1 || p->n_bl < 0) return KSP_EINVAL;
-    if (p->n_time > 4096 || p->n_freq > (1 << 22)) return KSP_ETOOLARGE;
+    if (p->n_time > 4096 || p->n_freq > (1 << 21)) return KSP_ETOOLARGE;
     if (p->average_freq < 1 || p->background_iterations < 1 || p->background_iterations > 63) return KSP_EINVAL;
     if (p->n_windows_time < 0 || p->n_windows_time > KSP_TWOD_MAX_WINDOWS) return KSP_EINVAL;
     if (p->n_windows_freq < 0 || p->n_windows_freq > KSP_TWOD_MAX_WINDOWS) return KSP_EINVAL;
@@ -631,6 +1284,22 @@ extern "C" size_t ksp_twodflag_scratch_bytes(const ksp_twodflag_params *p, int64
     return a.per_bl * (size_t) batch_baselines;
 }
 
+extern "C" int ksp_twodflag_resident_baselines(void)
+{
+    return TD_BLOCKS_PER_SM * ksp_sm_count();
+}
+
+extern "C" int ksp_twodflag_phases(unsigned long long *out, int n, int reset)
+{
+    if (n < 0 || n > KSP_TWOD_PHASES || (n > 0 && !out)) return KSP_EINVAL;
+    if (n > 0) KSP_CUDA(cudaMemcpyFromSymbol(out, td_phase, sizeof(unsigned long long) * (size_t) n));
+    if (reset) {
+        const unsigned long long zero[KSP_TWOD_PHASES] = {0};
+        KSP_CUDA(cudaMemcpyToSymbol(td_phase, zero, sizeof(zero)));
+    }
+    return 0;
+}
+
 extern "C" int ksp_twodflag(void *stream, const ksp_twodflag_params *p, const void *data,
                             const uint8_t *in_flags, uint8_t *out_flags, void *scratch, size_t scratch_bytes,
                             int64_t batch_baselines)
@@ -648,20 +1317,21 @@ extern "C" int ksp_twodflag(void *stream, const ksp_twodflag_params *p, const vo
     fill_derived(a);
     if (scratch_bytes < a.per_bl * (size_t) batch_baselines) return KSP_ESCRATCH;
     a.scratch = (char *) scratch;
-    const int resident = 4 * ksp_sm_count();
+    const int resident = TD_BLOCKS_PER_SM * ksp_sm_count();
     for (int64_t bl0 = 0; bl0 < p->n_bl; bl0 += batch_baselines) {
         a.bl0 = bl0;
         a.nb = p->n_bl - bl0 < batch_baselines ? p->n_bl - bl0 : batch_baselines;
-        const int64_t n_avg = a.nb * p->n_time * a.a_freq, n_out = a.nb * p->n_time * p->n_freq;
-        if (ksp_divup(n_avg, 256) > 0x7fffffff || ksp_divup(n_out, 256) > 0x7fffffff) return KSP_ETOOLARGE;
-        if (p->is_complex) twod_average_kernel<true><<<(unsigned) ksp_divup(n_avg, 256), 256, 0, s>>>(a);
-        else twod_average_kernel<false><<<(unsigned) ksp_divup(n_avg, 256), 256, 0, s>>>(a);
+        if (ksp_divup(a.nb, 32) > 0x7fffffff) return KSP_ETOOLARGE;
+        const dim3 g_avg((unsigned) ksp_divup(a.nb, 32), (unsigned) ksp_divup(a.a_freq, 32), (unsigned) p->n_time);
+        const dim3 g_out((unsigned) ksp_divup(a.nb, 32), (unsigned) ksp_divup(p->n_freq, 32), (unsigned) p->n_time);
+        if (p->is_complex) twod_average_kernel<true><<<g_avg, 256, 0, s>>>(a);
+        else twod_average_kernel<false><<<g_avg, 256, 0, s>>>(a);
         KSP_CHECK_LAUNCH();
         const int blocks = (int) (a.nb < resident ? a.nb : resident);
         twod_baseline_kernel<<<blocks, TD_THREADS, 0, s>>>(a);
         KSP_CHECK_LAUNCH();
-        if (p->is_complex) twod_output_kernel<true><<<(unsigned) ksp_divup(n_out, 256), 256, 0, s>>>(a);
-        else twod_output_kernel<false><<<(unsigned) ksp_divup(n_out, 256), 256, 0, s>>>(a);
+        if (p->is_complex) twod_output_kernel<true><<<g_out, 256, 0, s>>>(a);
+        else twod_output_kernel<false><<<g_out, 256, 0, s>>>(a);
         KSP_CHECK_LAUNCH();
     }
     return 0;

@@ -125,7 +125,7 @@ class SumThresholdFlagger:
         magnitudes); ``flags`` of the same shape marks samples to ignore.  Returns a bool array of
         that shape.  ``pool`` and ``is_multiprocess`` (the reference's CPU executors) are accepted
         and ignored; ``chunk_size`` is the number of baselines in flight on the device at a time
-        (default: enough to fill it, within ~4 GB of scratch).
+        (default: enough to fill it, within ~8 GB of scratch).
         """
         if data.shape != flags.shape:
             raise ValueError("Shape mismatch")
@@ -149,7 +149,7 @@ class SumThresholdFlagger:
             raise ValueError("parameters outside the supported range")
         n_bl = data.shape[2]
         if not chunk_size:
-            chunk_size = max(1, min(n_bl, 4 * 148, (4 << 30) // per_baseline))
+            chunk_size = max(1, min(n_bl, int(lib.ksp_twodflag_resident_baselines()), (8 << 30) // per_baseline))
         chunk_size = int(min(chunk_size, n_bl))
         d_data = accel.DeviceArray(context, host_data.shape, host_data.dtype)
         d_flags = accel.DeviceArray(context, host_flags.shape, np.uint8)

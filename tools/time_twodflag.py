@@ -54,7 +54,7 @@ def main():
     p = flagger._params(shape, True)
     lib = _capi.load()
     per_bl = int(lib.ksp_twodflag_scratch_bytes(byref(p), 1))
-    batch = max(1, min(shape[2], 4 * 148, (4 << 30) // per_bl))
+    batch = max(1, min(shape[2], int(lib.ksp_twodflag_resident_baselines()), (8 << 30) // per_bl))
     d_vis = accel.DeviceArray(context, vis.shape, vis.dtype)
     d_fl = accel.DeviceArray(context, vis.shape, np.uint8)
     d_out = accel.DeviceArray(context, vis.shape, np.uint8)
@@ -62,7 +62,10 @@ def main():
     d_vis.set(queue, vis)
     d_fl.set(queue, flags.astype(np.uint8))
     times = []
-    for _ in range(args.reps + 1):
+    phases = (ctypes.c_ulonglong * 20)()
+    for rep in range(args.reps + 1):
+        if rep == args.reps:
+            _capi.call("ksp_twodflag_phases", phases, 0, 1)
         a = queue.enqueue_marker()
         _capi.call("ksp_twodflag", ctypes.c_void_p(queue.stream), byref(p), ctypes.c_void_p(d_vis.buffer.ptr),
                    ctypes.c_void_p(d_fl.buffer.ptr), ctypes.c_void_p(d_out.buffer.ptr),
@@ -70,11 +73,19 @@ def main():
         b = queue.enqueue_marker()
         queue.finish()
         times.append(b.time_since(a))
+    _capi.call("ksp_twodflag_phases", phases, 20, 0)
+    names = ["spectrum median", "spectrum gaussians", "spectrum mad", "spectrum interpolate", "spectrum st thresholds",
+             "spectrum st lines", "2d gaussians", "2d mad", "2d interpolate", "st time", "st freq thresholds",
+             "st freq lines", "combine", "unaverage + fill", "-", "elementwise", "box time passes", "box freq passes",
+             "gaussian mask + normalise", "-"]
+    tot = float(sum(phases)) or 1.0
+    phase_tab = {n: round(int(c) / tot, 4) for n, c in zip(names, phases) if n != "-"}
+    phase_tab["cycles of block 0"] = int(tot)
     dev = sorted(times[1:])[len(times[1:]) // 2]
     res = {"shape": list(shape), "samples": n, "flagged_fraction": float(out.mean()),
            "gpu_device_s": dev, "gpu_device_Msamples_s": n / dev / 1e6,
            "gpu_end_to_end_s": e2e, "gpu_end_to_end_Msamples_s": n / e2e / 1e6, "first_call_s": first,
-           "scratch_MB_per_baseline": per_bl / 1e6, "baselines_in_flight": batch}
+           "scratch_MB_per_baseline": per_bl / 1e6, "baselines_in_flight": batch, "phase_share_block0_last_rep": phase_tab}
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     with open(os.environ.get("TK_OUT", "gpurun_out/time_twodflag.json"), "w") as f:
