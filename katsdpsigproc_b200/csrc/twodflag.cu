@@ -46,7 +46,6 @@ constexpr int TD_THREADS = 128;
 constexpr int TD_WARPS = TD_THREADS / 32;
 constexpr int TD_BLOCKS_PER_SM = 8;
 constexpr int TD_SMEM_WORDS = 5120;          // 20 KB of rings / tiles per block
-constexpr int TD_TILE_WORDS = 32 * 33;       // transposing tile of the frequency-axis box filter
 constexpr int TD_PASSES = 4;                 // box filters per Gaussian (reference default, twodflag.py:313)
 constexpr double TD_MAD_NORMAL = 1.4826;     // rfi/__init__.py:31
 constexpr unsigned FULL = 0xffffffffu;
@@ -408,10 +407,12 @@ __device__ float warp_median(const KeyAt &key_at, int n, uint32_t *hist, int lan
 // ring of its last 2 r inputs; all four rings turn together, so one slot number serves them.
 // The rings of stages 1 and 2 start as zeros (the padding), those of 3 and 4 are filled while
 // these stages sum their first 2 r inputs.
-// Inside one thread the stages are SKEWED by one step each: iteration `it` runs stage 1 at step
-// it, stage 2 at step it - 1 (on what stage 1 produced in the previous iteration), stage 3 at
-// step it - 2, stage 4 at step it - 3.  Nothing in an iteration then waits for anything else in
-// it - four independent dependency chains instead of one four times as long.
+// The four stages of a line are four neighbouring LANES (lane = 4 * line + stage): one thread
+// runs one stage, and hands what it produced to the next lane with a shuffle at the start of the
+// next iteration.  So the stages are skewed by one iteration each - iteration `it` runs stage 1
+// at step it, stage 2 at step it - 1, stage 3 at step it - 2, stage 4 at step it - 3 - and the
+// dependency chain of an iteration is one stage long; 32 lines keep all four warps of a block
+// (all four schedulers of the SM, each with its own float64 and conversion pipes) busy.
 // Two arithmetics.  BoxF64: the reference's - float64 sums, float32 between the stages.
 // BoxInt: the same sums as 32-bit integers, for lines whose samples are 0 or 1 (the weights of a
 // masked filter): every intermediate is an integer below (2 r + 1)^4, so for r <= 31 it is below
@@ -441,10 +442,99 @@ struct BoxInt {
 };
 constexpr int TD_INT_RADIUS = 31;                 // (2 * 31 + 1)^4 < 2^24
 
-// Inside one thread the stages are SKEWED by one step each: iteration `it` runs stage 1 at step
-// it, stage 2 at step it - 1 (on what stage 1 produced in the previous iteration), stage 3 at
-// step it - 2, stage 4 at step it - 3.  Nothing in an iteration then waits for anything else in
-// it - four independent dependency chains instead of one four times as long.
+// One stage of one line.  Stage p (0-based) runs its step it - p in iteration `it`, so with
+// `it` as the common clock: it adds its input while it < add_limit (stage 1: the n samples; stage
+// 2: n + 2 r values of stage 1; stages 3, 4: always), and it produces / pops from iteration
+// pop_start on (stages 1, 2: at once, their rings start as the zero padding; stage 3 after its
+// first 2 r inputs; stage 4 likewise) - before that `e` stays 0, which is a no-op downstream.
+template <typename A>
+struct BoxStage {
+    typename A::Sum s;
+    typename A::Val e;            // what this stage produced in the previous iteration
+    int add_limit, pop_start;
+    __device__ __forceinline__ void init(int p, int n, int r2)
+    {
+        s = 0;
+        e = 0;
+        add_limit = p == 0 ? n : p == 1 ? n + r2 + 1 : 0x7fffffff;
+        pop_start = p == 2 ? r2 + 2 : p == 3 ? 2 * r2 + 3 : 0;
+    }
+    // `in`: the sample (stage 1) or the previous lane's e; rp: this thread's ring slot it mod 2 r.
+    // Returns what the stage produced; it counts (and e takes it) from pop_start on.  Branch-free.
+    __device__ __forceinline__ typename A::Val step(int it, typename A::Val in, float *rp)
+    {
+        const bool add_ok = it < add_limit, pop_ok = it >= pop_start;
+        const typename A::Sum sa0 = A::add(s, in);
+        const typename A::Sum sa = add_ok ? sa0 : s;
+        const typename A::Val en = A::round(sa);
+        const typename A::Sum sb = A::sub(sa, A::load(rp));
+        s = pop_ok ? sb : sa;
+        e = pop_ok ? en : e;
+        A::store(rp, in);
+        return en;
+    }
+};
+
+// float32(2 r + 1) ** K as numba evaluates it: binary exponentiation in float32 (K = 4: the
+// square of the square)
+__device__ __forceinline__ float box_divisor(int r)
+{
+    static_assert(sizeof(TdArgs) % 4 == 0, "copied by words");
+    static_assert(TD_PASSES == 4, "square of the square");
+    const float d = (float) (2 * r + 1);
+    const float d2 = __fmul_rn(d, d);
+    return __fmul_rn(d2, d2);
+}
+
+// Lines of a ring-based pass that fit the shared memory: a multiple of 32 when at least 32 fit.
+__device__ __forceinline__ int td_lines_that_fit(int words_available, int words_per_line, int most)
+{
+    int L = words_available / words_per_line;
+    if (L > most) L = most;
+    if (L >= 32) L &= ~31;
+    return L;
+}
+
+__device__ __forceinline__ float td_shfl_up1(float v) { return __shfl_up_sync(FULL, v, 1); }
+__device__ __forceinline__ int td_shfl_up1(int v) { return __shfl_up_sync(FULL, v, 1); }
+
+// Time axis of a masked filter.  Lines 0 .. F - 1 are the weights of the columns (1 where
+// unflagged), lines F .. 2 F - 1 the data with flagged samples zeroed, both made on the fly from
+// `data` and `flags`; results into weight / out.  The samples of the next four iterations (and of
+// the thread's next line) are requested before the current four are worked on: the arrays live
+// in DRAM, and nothing else hides that latency.
+struct TimeLine {
+    const float *data;
+    const uint8_t *flags;
+    int T, F;
+    // Four raw samples of a line, t0 .. t0 + 3: the loads are only ISSUED here - masking them now
+    // would wait for them.
+    struct Raw {
+        float d[4];
+        uint8_t f[4];
+    };
+    __device__ __forceinline__ void load4(int line, int t0, Raw &r) const
+    {
+        const bool is_data = line >= F;
+        const int f = is_data ? line - F : line;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            r.d[k] = 1.0f;
+            r.f[k] = 1;
+            if (t0 + k < T) {
+                const int64_t o = (int64_t) (t0 + k) * F + f;
+                if (is_data) r.d[k] = data[o];
+                r.f[k] = flags[o];
+            }
+        }
+    }
+    static __device__ __forceinline__ float masked(const Raw &r, int k) { return r.f[k] ? 0.0f : r.d[k]; }
+};
+
+// The time-axis passes have thousands of short lines and use the same four stages inside ONE
+// thread per line (less work per line and iteration than four lanes and a shuffle; with that many
+// lines every warp is busy anyway).  Iteration `it` again runs stage 1 at step it, stage 2 at step
+// it - 1, ... so that nothing in an iteration waits for anything else in it.
 template <typename A>
 struct BoxState {
     typename A::Sum s1, s2, s3, s4;
@@ -500,80 +590,32 @@ __device__ __forceinline__ bool box_iter(BoxState<A> &st, float *rp, int pitch, 
     return d4;
 }
 
-// float32(2 r + 1) ** K as numba evaluates it: binary exponentiation in float32 (K = 4: the
-// square of the square)
-__device__ __forceinline__ float box_divisor(int r)
-{
-    static_assert(sizeof(TdArgs) % 4 == 0, "copied by words");
-    static_assert(TD_PASSES == 4, "square of the square");
-    const float d = (float) (2 * r + 1);
-    const float d2 = __fmul_rn(d, d);
-    return __fmul_rn(d2, d2);
-}
-
-// Lines of a ring-based pass that fit the shared memory: a multiple of 32 when at least 32 fit.
-__device__ __forceinline__ int td_lines_that_fit(int words_available, int words_per_line, int most)
-{
-    int L = words_available / words_per_line;
-    if (L > most) L = most;
-    if (L >= 32) L &= ~31;
-    return L;
-}
-
-// Time axis of a masked filter: one thread per line - lines 0 .. F - 1 the weights of the
-// columns (1 where unflagged), lines F .. 2 F - 1 the data with flagged samples zeroed, both made
-// on the fly from `data` and `flags` - L lines at a time, results into weight / out.  The inputs
-// of the next eight iterations (and of the thread's next line) are requested before the current
-// eight are worked on: the arrays live in DRAM, and nothing else hides that latency.
-struct TimeLine {
-    const float *data;
-    const uint8_t *flags;
-    int T, F;
-    __device__ __forceinline__ void load8(int line, int t0, float (&v)[8]) const
-    {
-        const bool is_data = line >= F;
-        const int f = is_data ? line - F : line;
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            float x = 0.0f;
-            if (t0 + k < T) {
-                const int64_t o = (int64_t) (t0 + k) * F + f;
-                x = is_data ? data[o] : 1.0f;
-                if (flags[o]) x = 0.0f;
-            }
-            v[k] = x;
-        }
-    }
-};
-
+// One line by one thread.  cur: its first four samples.  ring: slot s of stage q at
+// ring[(q * r2 + s) * L].
 template <typename A>
-__device__ __forceinline__ void box_time_line(const TimeLine &in, int line, float (&v)[8], float *dst, float *ring,
-                                              int L, int r2, float div)
+__device__ __forceinline__ void box_time_line(const TimeLine &in, int line, TimeLine::Raw &cur, float *dst,
+                                              float *ring, int L, int r2, float div)
 {
-    const int T = in.T, F = in.F, len = T + 2 * r2, pitch = r2 * L;
+    const int T = in.T, F = in.F, total = T + 2 * r2 + 3, out_start = 2 * r2 + 3, pitch = r2 * L;
     for (int s = 0; s < 4 * r2; s++) ring[s * L] = 0.0f;                  // all four rings (0 in either arithmetic)
     BoxState<A> st = {0, 0, 0, 0, 0, 0, 0};
     int slot = 0;
-    for (int it0 = 0; it0 < len + 3; it0 += 8) {
-        float v2[8];
-        if (it0 + 8 < T) {
-            in.load8(line, it0 + 8, v2);
-        } else {
+    for (int it0 = 0; it0 < total; it0 += 4) {
+        TimeLine::Raw next;
 #pragma unroll
-            for (int k = 0; k < 8; k++) v2[k] = 0.0f;
-        }
+        for (int k = 0; k < 4; k++) next.f[k] = 1;
+        if (it0 + 4 < T) in.load4(line, it0 + 4, next);
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < 4; k++) {
             const int it = it0 + k;
-            if (it < len + 3) {
+            if (it < total) {
                 float o;
-                if (box_iter<A>(st, ring + slot * L, pitch, it, T, r2, v[k], o))
-                    dst[(int64_t) (it - 3 - 2 * r2) * F] = __fdiv_rn(o, div);
+                box_iter<A>(st, ring + slot * L, pitch, it, T, r2, TimeLine::masked(cur, k), o);
+                if (it >= out_start) dst[(int64_t) (it - out_start) * F] = __fdiv_rn(o, div);
                 slot = (slot + 1 == r2) ? 0 : slot + 1;
             }
         }
-#pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = v2[k];
+        cur = next;
     }
 }
 
@@ -585,21 +627,21 @@ __device__ __noinline__ void box_time_pass(const float *__restrict__ data, const
     const float div = box_divisor(r);
     const int lines = 2 * F;
     const TimeLine in = {data, flags, T, F};
-    float nxt[8];
-    if (tid < L && tid < lines) in.load8(tid, 0, nxt);
+    TimeLine::Raw nxt;
+#pragma unroll
+    for (int k = 0; k < 4; k++) nxt.f[k] = 1;
+    if (tid < L && tid < lines) in.load4(tid, 0, nxt);
     for (int base = 0; base < lines; base += L) {
         const int line = base + tid;
         if (tid < L && line < lines) {
-            float v[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) v[k] = nxt[k];
-            if (line + L < lines) in.load8(line + L, 0, nxt);             // the next round's first inputs
+            TimeLine::Raw cur = nxt;
+            if (line + L < lines) in.load4(line + L, 0, nxt);             // the next round's first samples
             float *ring = s_sm + tid;
             if (line < F) {
-                if (r <= TD_INT_RADIUS) box_time_line<BoxInt>(in, line, v, weight + line, ring, L, r2, div);
-                else box_time_line<BoxF64>(in, line, v, weight + line, ring, L, r2, div);
+                if (r <= TD_INT_RADIUS) box_time_line<BoxInt>(in, line, cur, weight + line, ring, L, r2, div);
+                else box_time_line<BoxF64>(in, line, cur, weight + line, ring, L, r2, div);
             } else {
-                box_time_line<BoxF64>(in, line, v, out + (line - F), ring, L, r2, div);
+                box_time_line<BoxF64>(in, line, cur, out + (line - F), ring, L, r2, div);
             }
         }
     }
@@ -613,87 +655,99 @@ __device__ __forceinline__ void cp_async4(float *smem_dst, const float *src, boo
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(bytes) : "memory");
 }
 
-// Frequency axis of a masked filter.  A warp takes L <= 32 lines - pairs (weights of row t, data
-// of row t) - and moves them through 32 x 32 transposing tiles: rows of 128 bytes in (cp.async,
-// the next tile in flight while this one is worked on), lane <-> line inside.  FROM_MASK: the
-// lines are made on the fly from `data` and `flags` (no time-axis pass before this one), else
-// they are weight / out as the time-axis pass left them.  The results leave through the tile
-// they came in by, 4 r + 3 positions behind the reads, already normalised: out = filtered data /
-// filtered weight, NaN where that weight is 0 (twodflag.py:392-399); `weight` is not written.
+// Frequency axis of a masked filter.  Lines are pairs (weights of row t, data of row t); a block
+// takes L <= 32 of them at a time, 8 per warp, and moves them through transposing tiles: rows of
+// 128 bytes in (cp.async, the next tile in flight while this one is worked on), one column per
+// iteration inside.  FROM_MASK: the lines are made on the fly from `data` and `flags` (no
+// time-axis pass before this one), else they are weight / out as the time-axis pass left them.
+// The results leave through the tile they came in by, 4 r + 3 positions behind the reads, already
+// normalised: out = filtered data / filtered weight, NaN where that weight is 0
+// (twodflag.py:392-399); `weight` is not written.
 template <bool FROM_MASK>
 __device__ __noinline__ void box_freq_pass(const float *__restrict__ data, const uint8_t *__restrict__ flags,
                                            const float *weight, float *out, int T, int F, int r)
 {
-    float *sm = s_sm;
     const int tid = td_vtid(), lane = tid & 31, warp = tid >> 5, r2 = 2 * r;
     const int lines = 2 * T;
-    int L = td_lines_that_fit(TD_SMEM_WORDS - 2 * TD_TILE_WORDS, 4 * r2, 32) & ~1;
-    if (L > lines) L = lines;
-    const int per_warp = 2 * TD_TILE_WORDS + 4 * r2 * L;
-    int conc = TD_SMEM_WORDS / per_warp;                 // warps that can work at the same time
-    if (conc > TD_WARPS) conc = TD_WARPS;
+    // per line: its four rings and a row in each of the two tiles
+    int L = td_lines_that_fit(TD_SMEM_WORDS, 4 * r2 + 66, TD_THREADS / 4) & ~1;
     const float div = box_divisor(r);
-    const int len = F + 2 * r2, pitch = r2 * L, total = len + 3;
-    const int groups = (lines + L - 1) / L;
-    if (warp < conc) {
-        float *tiles = sm + warp * per_warp, *ring = tiles + 2 * TD_TILE_WORDS + lane;
-        for (int g = warp; g < groups; g += conc) {
-            const int first = g * L, nl = min(L, lines - first);
-            const bool active = lane < nl;
-            // request the tile of iterations step0 .. step0 + 31 (one commit group per tile)
-            auto request = [&](float *tile, int step0) {
-                const int idx = step0 + lane;
-                const bool inside = idx < F;
-                for (int ll = 0; ll < nl; ll++) {
-                    const int line = first + ll;
-                    const int64_t row = (int64_t) (line >> 1) * F;
-                    if (FROM_MASK) {
-                        float x = 0.0f;
-                        if (inside) {
-                            x = (line & 1) ? data[row + idx] : 1.0f;
-                            if (flags[row + idx]) x = 0.0f;
-                        }
-                        tile[ll * 33 + lane] = x;
-                    } else {
-                        const float *src = ((line & 1) ? out : weight) + row;
-                        cp_async4(tile + ll * 33 + lane, src + (inside ? idx : 0), inside);
+    const int total = F + 2 * r2 + 3;
+    const int ll = tid >> 2, p = tid & 3;                 // this thread's line of the group, and its stage
+    float *tiles = s_sm, *ring = s_sm + 2 * L * 33 + tid;
+    const int rstride = 4 * L;
+    const int ll0 = warp * 8;                             // the warp's lines: ll0 .. ll0 + 7
+    for (int first = 0; first < lines; first += L) {
+        const int nl = min(L, lines - first);             // lines of this group
+        const int mine = max(0, min(8, nl - ll0));        // of which this warp's
+        if (mine == 0) continue;                          // warp-uniform
+        const bool active = ll < nl;
+        // request the tile of iterations step0 .. step0 + 31 (one commit group per tile)
+        auto request = [&](float *tile, int step0) {
+            const int idx = step0 + lane;
+            const bool inside = idx < F;
+            for (int j = 0; j < mine; j++) {
+                const int line = first + ll0 + j;
+                const int64_t row = (int64_t) (line >> 1) * F;
+                float *dstw = tile + (ll0 + j) * 33 + lane;
+                if (FROM_MASK) {
+                    float x = 0.0f;
+                    if (inside) {
+                        x = (line & 1) ? data[row + idx] : 1.0f;
+                        if (flags[row + idx]) x = 0.0f;
                     }
-                }
-                asm volatile("cp.async.commit_group;" ::: "memory");
-            };
-            if (active)
-                for (int s = 0; s < 4 * r2; s++) ring[s * L] = 0.0f;
-            BoxState<BoxF64> st = {0.0, 0.0, 0.0, 0.0, 0.0f, 0.0f, 0.0f};
-            int slot = 0, tb = 0;
-            request(tiles, 0);
-            for (int step0 = 0; step0 < total; step0 += 32, tb ^= 1) {
-                float *tile = tiles + tb * TD_TILE_WORDS;
-                if (step0 + 32 < total) {
-                    request(tiles + (tb ^ 1) * TD_TILE_WORDS, step0 + 32);
-                    asm volatile("cp.async.wait_group 1;" ::: "memory");
+                    *dstw = x;
                 } else {
-                    asm volatile("cp.async.wait_group 0;" ::: "memory");
+                    const float *src = ((line & 1) ? out : weight) + row;
+                    cp_async4(dstw, src + (inside ? idx : 0), inside);
                 }
-                __syncwarp();
-                if (active) {
-                    const int kmax = min(32, total - step0);
-                    for (int k = 0; k < kmax; k++) {
-                        float o = 0.0f;
-                        const bool done = box_iter<BoxF64>(st, ring + slot * L, pitch, step0 + k, F, r2, tile[lane * 33 + k], o);
-                        tile[lane * 33 + k] = done ? __fdiv_rn(o, div) : 0.0f;
-                        slot = (slot + 1 == r2) ? 0 : slot + 1;
-                    }
-                }
-                __syncwarp();
-                const int oi = step0 + lane - 3 - 2 * r2;            // line position of what sits in column `lane`
-                if (oi >= 0 && oi < F) {
-                    for (int ll = 0; ll < nl; ll += 2) {
-                        const float w = tile[ll * 33 + lane], d = tile[(ll + 1) * 33 + lane];
-                        out[(int64_t) ((first + ll) >> 1) * F + oi] = (w == 0.0f) ? td_nan() : __fdiv_rn(d, w);
-                    }
-                }
-                __syncwarp();
             }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        if (active)
+            for (int s = 0; s < r2; s++) ring[s * rstride] = 0.0f;
+        BoxStage<BoxF64> st;
+        st.init(p, F, r2);
+        const bool head = active && p == 0, tail = active && p == 3;
+        float *rp = ring;
+        int slot = 0, tb = 0;
+        request(tiles, 0);
+        for (int step0 = 0; step0 < total; step0 += 32, tb ^= 1) {
+            float *tile = tiles + tb * L * 33;
+            if (step0 + 32 < total) {
+                request(tiles + (tb ^ 1) * L * 33, step0 + 32);
+                asm volatile("cp.async.wait_group 1;" ::: "memory");
+            } else {
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+            }
+            __syncwarp();
+            float *cell = tile + ll * 33;
+            const int kmax = min(32, total - step0);
+            for (int k = 0; k < kmax; k++) {
+                const float from_prev = td_shfl_up1(st.e);
+                const float x = head ? cell[k] : from_prev;
+                if (active) {
+                    const int it = step0 + k;
+                    const float en = st.step(it, x, rp);
+                    if (tail) cell[k] = en;                            // unnormalised; only positions >= 0 are used
+                }
+                slot++;
+                rp += rstride;
+                if (slot == r2) {
+                    slot = 0;
+                    rp = ring;
+                }
+            }
+            __syncwarp();
+            const int oi = step0 + lane - 3 - 2 * r2;            // line position of what sits in column `lane`
+            if (oi >= 0 && oi < F) {
+                for (int j = 0; j < mine; j += 2) {
+                    const float w = __fdiv_rn(tile[(ll0 + j) * 33 + lane], div);
+                    const float d = __fdiv_rn(tile[(ll0 + j + 1) * 33 + lane], div);
+                    out[(int64_t) ((first + ll0 + j) >> 1) * F + oi] = (w == 0.0f) ? td_nan() : __fdiv_rn(d, w);
+                }
+            }
+            __syncwarp();
         }
     }
     __syncthreads();
@@ -730,8 +784,8 @@ __device__ __noinline__ void masked_gaussian(const float *data, const uint8_t *f
                                              float *out, float *weight)
 {
     const int tid = threadIdx.x, A = T * F;
-    const bool time_ring = r_t > 0 && 8 * r_t <= TD_SMEM_WORDS;
-    const bool freq_ring = r_f > 0 && 8 * r_f <= TD_SMEM_WORDS - 2 * TD_TILE_WORDS;
+    const bool time_ring = r_t > 0 && 8 * r_t <= TD_SMEM_WORDS;                 // a line fits
+    const bool freq_ring = r_f > 0 && 2 * (8 * r_f + 66) <= TD_SMEM_WORDS;     // 2 lines fit
     const bool masked_first = time_ring || (r_t == 0 && freq_ring);
     if (!masked_first) {
         for (int i = tid; i < A; i += TD_THREADS) {
@@ -1244,7 +1298,7 @@ void fill_derived(TdArgs &a)
         const int cl = (int) (a.p.chunk_ends[c + 1] - a.p.chunk_ends[c]);
         if (cl > a.max_cl) a.max_cl = cl;
     }
-    a.big_radius = 8 * a.max_rt > TD_SMEM_WORDS || 8 * a.max_rf > TD_SMEM_WORDS - 2 * TD_TILE_WORDS;
+    a.big_radius = 8 * a.max_rt > TD_SMEM_WORDS || 2 * (8 * a.max_rf + 66) > TD_SMEM_WORDS;
     a.per_bl = td_layout(a, nullptr, nullptr);
 }
 
