@@ -65,6 +65,7 @@ class SumThresholdFlagger:
         self.rho = rho
         self._context = context
         self._queue: Any = None
+        self._buffers: dict = {}
 
     # ------------------------------------------------------------------ parameters for the C ABI
     def _params(self, shape: Sequence[int], is_complex: bool) -> "_capi.TwodflagParams":
@@ -132,13 +133,61 @@ class SumThresholdFlagger:
         if data.ndim != 3:
             raise ValueError("data has wrong number of dimensions")
         is_complex = np.iscomplexobj(data)
-        host_data = np.ascontiguousarray(data, np.complex64 if is_complex else np.float32)
-        host_flags = np.ascontiguousarray(flags).astype(np.uint8, copy=False)
-        if host_flags.dtype != np.uint8 or flags.dtype != np.bool_:
-            host_flags = (np.ascontiguousarray(flags) != 0).astype(np.uint8)
-        out = np.empty(data.shape, np.bool_)
         if data.size == 0:
-            return out
+            return np.empty(data.shape, np.bool_)
+        p = self._params(data.shape, is_complex)
+        queue = self._ensure_queue()
+        context = queue.context
+        lib = _capi.load()
+        context._make_current()
+        per_baseline = int(lib.ksp_twodflag_scratch_bytes(byref(p), 1))
+        if per_baseline == 0:
+            raise ValueError("parameters outside the supported range")
+        n_bl = data.shape[2]
+        if not chunk_size:
+            chunk_size = max(1, min(n_bl, int(lib.ksp_twodflag_resident_baselines()),
+                                    (8 << 30) // per_baseline))
+        chunk_size = int(min(chunk_size, n_bl))
+        buf = self._buffers_for(context, data.shape, np.complex64 if is_complex else np.float32,
+                                per_baseline * chunk_size)
+        # into the pinned staging arrays (the conversions of dtype / layout happen in these copies)
+        np.copyto(buf["h_data"], data, casting="unsafe")
+        if flags.dtype == np.bool_:
+            np.copyto(buf["h_flags"].view(np.bool_), flags)
+        else:
+            np.not_equal(flags, 0, out=buf["h_flags"].view(np.bool_))
+        buf["d_data"].set_async(queue, buf["h_data"])
+        buf["d_flags"].set_async(queue, buf["h_flags"])
+        _capi.call("ksp_twodflag", ctypes.c_void_p(queue.stream), byref(p),
+                   ctypes.c_void_p(buf["d_data"].buffer.ptr), ctypes.c_void_p(buf["d_flags"].buffer.ptr),
+                   ctypes.c_void_p(buf["d_out"].buffer.ptr), ctypes.c_void_p(buf["d_scratch"].buffer.ptr),
+                   c_size_t(per_baseline * chunk_size), ctypes.c_int64(chunk_size))
+        buf["d_out"].get_async(queue, buf["h_out"])
+        queue.finish()
+        return np.array(buf["h_out"].view(np.bool_))               # the kernel writes 0 / 1: a copy the caller owns
+
+    def _buffers_for(self, context: Any, shape: Sequence[int], dtype: Any, scratch_bytes: int) -> dict:
+        """Device arrays and pinned staging arrays for one input shape, kept from call to call
+        (``get_flags`` is called again and again with blocks of the same shape; allocating
+        pinned and device memory costs more than the flagging)."""
+        key = (tuple(shape), np.dtype(dtype).str)
+        buf = self._buffers.get("arrays")
+        if buf is None or buf["key"] != key:
+            self._buffers.clear()
+            buf = {"key": key}
+            buf["h_data"] = accel.HostArray(tuple(shape), dtype, context=context)
+            buf["h_flags"] = accel.HostArray(tuple(shape), np.uint8, context=context)
+            buf["h_out"] = accel.HostArray(tuple(shape), np.uint8, context=context)
+            buf["d_data"] = accel.DeviceArray(context, tuple(shape), dtype)
+            buf["d_flags"] = accel.DeviceArray(context, tuple(shape), np.uint8)
+            buf["d_out"] = accel.DeviceArray(context, tuple(shape), np.uint8)
+            buf["d_scratch"] = None
+            self._buffers["arrays"] = buf
+        if buf["d_scratch"] is None or buf["d_scratch"].shape[0] < scratch_bytes:
+            buf["d_scratch"] = None                                # release before the larger allocation
+            buf["d_scratch"] = accel.DeviceArray(context, (scratch_bytes,), np.uint8)
+        return buf
+
         p = self._params(data.shape, is_complex)
         queue = self._ensure_queue()
         context = queue.context
