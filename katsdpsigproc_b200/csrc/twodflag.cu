@@ -319,24 +319,29 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, int lane)
 // Median of the non-skipped keys of a set, by ONE warp: exact radix select on the bit patterns of
 // non-negative floats, 4 passes of 8 bits with a 256-bin histogram of the warp's own, then (even
 // counts) one pass for the next key above; float32 mean of the two middle values as numba's
-// np.median of float32.  key_at(i), i < n, returns KEY_SKIP for elements that take no part.
-// NaN if the set is empty.  All lanes return the same value.
+// np.median of float32.  The set is rows x cols; key_at(r, c) returns KEY_SKIP for elements that
+// take no part.  NaN if the set is empty.  All lanes return the same value.
 template <typename KeyAt>
-__device__ float warp_median(const KeyAt &key_at, int n, uint32_t *hist, int lane)
+__device__ float warp_median(const KeyAt &key_at, int rows, int cols, uint32_t *hist, int lane)
 {
     uint32_t prefix = 0, prefix_mask = 0, rank = 0, n_valid = 0;
 #pragma unroll 1
     for (int shift = 24; shift >= 0; shift -= 8) {
         for (int bin = lane; bin < 256; bin += 32) hist[bin] = 0u;
         __syncwarp();
-        for (int i = lane; i < n; i += 128) {                      // four loads in flight per lane
-            uint32_t k[4];
+        for (int r = 0; r < rows; r += 2)
+            for (int c = lane; c < cols; c += 128) {                // eight loads in flight per lane
+                uint32_t k[8];
 #pragma unroll
-            for (int u = 0; u < 4; u++) k[u] = (i + 32 * u < n) ? key_at(i + 32 * u) : KEY_SKIP;
+                for (int u = 0; u < 4; u++) {
+                    k[u] = (c + 32 * u < cols) ? key_at(r, c + 32 * u) : KEY_SKIP;
+                    k[4 + u] = (r + 1 < rows && c + 32 * u < cols) ? key_at(r + 1, c + 32 * u) : KEY_SKIP;
+                }
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (k[u] != KEY_SKIP && (k[u] & prefix_mask) == prefix) atomicAdd(&hist[(k[u] >> shift) & 0xffu], 1u);
-        }
+                for (int u = 0; u < 8; u++)
+                    if (k[u] != KEY_SKIP && (k[u] & prefix_mask) == prefix)
+                        atomicAdd(&hist[(k[u] >> shift) & 0xffu], 1u);
+            }
         __syncwarp();
         uint32_t c[8], tot = 0;
 #pragma unroll
@@ -374,17 +379,18 @@ __device__ float warp_median(const KeyAt &key_at, int n, uint32_t *hist, int lan
     uint32_t hi = lo;
     if (!(n_valid & 1u)) {
         uint32_t best = KEY_SKIP, cnt = 0;
-        for (int i = lane; i < n; i += 128) {
-            uint32_t k[4];
+        for (int r = 0; r < rows; r++)
+            for (int c = lane; c < cols; c += 128) {
+                uint32_t k[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) k[u] = (i + 32 * u < n) ? key_at(i + 32 * u) : KEY_SKIP;
+                for (int u = 0; u < 4; u++) k[u] = (c + 32 * u < cols) ? key_at(r, c + 32 * u) : KEY_SKIP;
 #pragma unroll
-            for (int u = 0; u < 4; u++)
-                if (k[u] != KEY_SKIP) {
-                    if (k[u] <= lo) cnt++;
-                    else best = min(best, k[u]);
-                }
-        }
+                for (int u = 0; u < 4; u++)
+                    if (k[u] != KEY_SKIP) {
+                        if (k[u] <= lo) cnt++;
+                        else best = min(best, k[u]);
+                    }
+            }
         best = __reduce_min_sync(FULL, best);
         cnt = __reduce_add_sync(FULL, cnt);
         if (cnt < ((n_valid - 1) >> 1) + 2) hi = best;              // rank k + 1 is the next distinct key
@@ -496,7 +502,6 @@ __device__ __forceinline__ int td_lines_that_fit(int words_available, int words_
 }
 
 __device__ __forceinline__ float td_shfl_up1(float v) { return __shfl_up_sync(FULL, v, 1); }
-__device__ __forceinline__ int td_shfl_up1(int v) { return __shfl_up_sync(FULL, v, 1); }
 
 // Time axis of a masked filter.  Lines 0 .. F - 1 are the weights of the columns (1 where
 // unflagged), lines F .. 2 F - 1 the data with flagged samples zeroed, both made on the fly from
@@ -919,14 +924,11 @@ __device__ __noinline__ void background2d(bool spectrum, int ph)
                     bg[o] = fabsf(__fsub_rn(data[o], bg[o]));
                 }
             __syncwarp();
-            const int rows32 = (cl + 31) / 32 * 32;                  // whole warps per row: coalesced
-            auto key_at = [=](int i) -> uint32_t {
-                const int t = i / rows32, j = i - t * rows32;
-                if (j >= cl) return KEY_SKIP;
+            auto key_at = [=](int t, int j) -> uint32_t {
                 const int o = t * F + c0 + j;
                 return work[o] ? KEY_SKIP : __float_as_uint(bg[o]);   // residuals are >= 0
             };
-            const float med = warp_median(key_at, T * rows32, s_whist + warp * 256, lane);
+            const float med = warp_median(key_at, T, cl, s_whist + warp * 256, lane);
             const double threshold = __dmul_rn((double) med, __dmul_rn(TD_MAD_NORMAL, a.p.background_reject));
             for (int t = 0; t < T; t++)
                 for (int j = lane; j < cl; j += 32) {
@@ -1047,10 +1049,10 @@ __device__ __noinline__ void sum_threshold_freq(bool spectrum, int ph)
         const int c0 = (int) a.p.chunk_ends[c], cl = (int) a.p.chunk_ends[c + 1] - c0;
         const float *row = data + (int64_t) t * F + c0;
         const uint8_t *frow = flags + (int64_t) t * F + c0;
-        auto key_at = [=](int j) -> uint32_t {
+        auto key_at = [=](int, int j) -> uint32_t {
             return frow[j] ? KEY_SKIP : (__float_as_uint(row[j]) & 0x7fffffffu);
         };
-        const float med = warp_median(key_at, cl, s_whist + warp * 256, lane);
+        const float med = warp_median(key_at, 1, cl, s_whist + warp * 256, lane);
         if (lane == 0) b.thr[i] = scaled_threshold(med, a.p.outlier_nsigma);
     }
     __syncthreads();

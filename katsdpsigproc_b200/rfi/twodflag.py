@@ -15,6 +15,7 @@ the library, not silently.
 
 from __future__ import annotations
 
+import concurrent.futures
 import ctypes
 from ctypes import byref, c_size_t
 from typing import Any, Optional, Sequence
@@ -22,6 +23,18 @@ from typing import Any, Optional, Sequence
 import numpy as np
 
 from .. import _capi, accel
+
+
+_STAGING_THREADS = 8
+_pool: Optional[concurrent.futures.ThreadPoolExecutor] = None
+
+
+def _staging_pool() -> concurrent.futures.ThreadPoolExecutor:
+    """Threads that copy large inputs into the pinned staging arrays (created on first use)."""
+    global _pool
+    if _pool is None:
+        _pool = concurrent.futures.ThreadPoolExecutor(_STAGING_THREADS, thread_name_prefix="twodflag-stage")
+    return _pool
 
 
 def _as_min_dtype(value: int) -> np.generic:
@@ -151,11 +164,22 @@ class SumThresholdFlagger:
         buf = self._buffers_for(context, data.shape, np.complex64 if is_complex else np.float32,
                                 per_baseline * chunk_size)
         # into the pinned staging arrays (the conversions of dtype / layout happen in these copies)
-        np.copyto(buf["h_data"], data, casting="unsafe")
-        if flags.dtype == np.bool_:
-            np.copyto(buf["h_flags"].view(np.bool_), flags)
+        h_flags = buf["h_flags"].view(np.bool_)
+
+        def stage(rows: slice) -> None:
+            np.copyto(buf["h_data"][rows], data[rows], casting="unsafe")
+            if flags.dtype == np.bool_:
+                np.copyto(h_flags[rows], flags[rows])
+            else:
+                np.not_equal(flags[rows], 0, out=h_flags[rows])
+
+        n_time = data.shape[0]
+        workers = min(_STAGING_THREADS, n_time) if data.nbytes >= (64 << 20) else 1
+        if workers > 1:                                            # numpy copies release the GIL
+            bounds = np.linspace(0, n_time, workers + 1).astype(int)
+            list(_staging_pool().map(stage, [slice(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:])]))
         else:
-            np.not_equal(flags, 0, out=buf["h_flags"].view(np.bool_))
+            stage(slice(None))
         buf["d_data"].set_async(queue, buf["h_data"])
         buf["d_flags"].set_async(queue, buf["h_flags"])
         _capi.call("ksp_twodflag", ctypes.c_void_p(queue.stream), byref(p),
