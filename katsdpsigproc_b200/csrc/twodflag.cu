@@ -413,12 +413,16 @@ __device__ float warp_median(const KeyAt &key_at, int rows, int cols, uint32_t *
 // ring of its last 2 r inputs; all four rings turn together, so one slot number serves them.
 // The rings of stages 1 and 2 start as zeros (the padding), those of 3 and 4 are filled while
 // these stages sum their first 2 r inputs.
-// The four stages of a line are four neighbouring LANES (lane = 4 * line + stage): one thread
-// runs one stage, and hands what it produced to the next lane with a shuffle at the start of the
-// next iteration.  So the stages are skewed by one iteration each - iteration `it` runs stage 1
-// at step it, stage 2 at step it - 1, stage 3 at step it - 2, stage 4 at step it - 3 - and the
-// dependency chain of an iteration is one stage long; 32 lines keep all four warps of a block
-// (all four schedulers of the SM, each with its own float64 and conversion pipes) busy.
+//
+// The stages are SKEWED by one iteration each - iteration `it` runs stage 1 at step it, stage 2
+// at step it - 1 (on what stage 1 produced in the previous iteration), stage 3 at step it - 2,
+// stage 4 at step it - 3 - so that nothing in an iteration waits for anything else in it.  Two
+// layouts: along frequency (2 T long lines) the four stages of a line are four neighbouring LANES
+// (lane = 4 * line + stage; a shuffle hands a stage's output to the next lane at the start of the
+// next iteration), so that 32 lines keep all four warps of a block - all four schedulers of the
+// SM, each with its own float64 and conversion pipes - busy; along time (2 F short lines) one
+// thread runs all four stages of a line as four independent chains in one branch-free block.
+//
 // Two arithmetics.  BoxF64: the reference's - float64 sums, float32 between the stages.
 // BoxInt: the same sums as 32-bit integers, for lines whose samples are 0 or 1 (the weights of a
 // masked filter): every intermediate is an integer below (2 r + 1)^4, so for r <= 31 it is below
