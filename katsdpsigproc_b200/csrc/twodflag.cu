@@ -317,86 +317,158 @@ __device__ __forceinline__ uint32_t warp_scan_incl(uint32_t v, int lane)
 }
 
 // Median of the non-skipped keys of a set, by ONE warp: exact radix select on the bit patterns of
-// non-negative floats, 4 passes of 8 bits with a 256-bin histogram of the warp's own, then (even
-// counts) one pass for the next key above; float32 mean of the two middle values as numba's
-// np.median of float32.  The set is rows x cols; key_at(r, c) returns KEY_SKIP for elements that
-// take no part.  NaN if the set is empty.  All lanes return the same value.
-template <typename KeyAt>
-__device__ float warp_median(const KeyAt &key_at, int rows, int cols, uint32_t *hist, int lane)
+// non-negative floats, 4 passes of 8 bits with a 256-bin histogram of the warp's own; float32 mean
+// of the two middle values as numba's np.median of float32.  NaN if the set is empty.  All lanes
+// return the same value.
+//
+// The end of a pass: which bin holds `rank`, and the rank inside it.  c: the lane's 8 bins.
+struct BinChoice {
+    uint32_t bin, r_in, count, total;
+};
+__device__ __forceinline__ BinChoice warp_choose_bin(const uint32_t *hist, uint32_t rank, bool first, int lane,
+                                                     uint32_t (&c)[8])
 {
-    uint32_t prefix = 0, prefix_mask = 0, rank = 0, n_valid = 0;
+    uint32_t tot = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        c[j] = hist[8 * lane + j];
+        tot += c[j];
+    }
+    const uint32_t incl = warp_scan_incl(tot, lane), excl = incl - tot;
+    BinChoice ch;
+    ch.total = __shfl_sync(FULL, incl, 31);
+    if (first) rank = ch.total ? (ch.total - 1) >> 1 : 0;          // the lower median
+    const bool mine = rank >= excl && rank < incl;
+    const int src = __ffs(__ballot_sync(FULL, mine)) - 1;
+    uint32_t bin = 0, r_in = 0, cnt = 0;
+    if (mine) {
+        uint32_t e = excl;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            if (rank >= e && rank < e + c[j]) {
+                bin = 8u * (uint32_t) lane + j;
+                r_in = rank - e;
+                cnt = c[j];
+            }
+            e += c[j];
+        }
+    }
+    ch.bin = __shfl_sync(FULL, bin, max(src, 0));
+    ch.r_in = __shfl_sync(FULL, r_in, max(src, 0));
+    ch.count = __shfl_sync(FULL, cnt, max(src, 0));
+    return ch;
+}
+
+// Upper median once the lower one (lo: the key `prefix24 | bin` with `count` copies, of which
+// number r_in is the lower median) is known: lo itself if another copy follows, else the next key
+// - the next occupied bin of the last pass's histogram (same upper 24 bits), else `beyond`, the
+// smallest key above all keys that share lo's upper 24 bits (collected during the last pass).
+__device__ __forceinline__ uint32_t warp_upper_median(uint32_t lo, const BinChoice &ch, const uint32_t (&c)[8],
+                                                      uint32_t beyond, int lane)
+{
+    if (ch.r_in + 1 < ch.count) return lo;
+    uint32_t next_bin = 0xffffffffu;
+#pragma unroll
+    for (int j = 7; j >= 0; j--) {
+        const uint32_t b = 8u * (uint32_t) lane + j;
+        if (c[j] != 0u && b > ch.bin) next_bin = b;
+    }
+    next_bin = __reduce_min_sync(FULL, next_bin);
+    if (next_bin != 0xffffffffu) return (lo & 0xffffff00u) | next_bin;
+    return __reduce_min_sync(FULL, beyond);
+}
+
+__device__ __forceinline__ float warp_median_finish(uint32_t lo, uint32_t hi)
+{
+    const float a = __uint_as_float(lo), b = __uint_as_float(hi);
+    return lo == hi ? a : __fmul_rn(__fadd_rn(a, b), 0.5f);
+}
+
+// The set is rows x cols in memory: key_first(r, c) is called for every element in the first
+// pass (it may compute and store what key_at(r, c) then re-reads in the other three); both return
+// KEY_SKIP for elements that take no part.  Eight loads in flight per lane.
+template <typename KeyFirst, typename KeyAt>
+__device__ float warp_median(const KeyFirst &key_first, const KeyAt &key_at, int rows, int cols, uint32_t *hist,
+                             int lane)
+{
+    uint32_t prefix = 0, prefix_mask = 0, rank = 0, n_valid = 0, beyond = KEY_SKIP;
+    uint32_t c[8];
+    BinChoice ch;
 #pragma unroll 1
     for (int shift = 24; shift >= 0; shift -= 8) {
         for (int bin = lane; bin < 256; bin += 32) hist[bin] = 0u;
         __syncwarp();
         for (int r = 0; r < rows; r += 2)
-            for (int c = lane; c < cols; c += 128) {                // eight loads in flight per lane
+            for (int col = lane; col < cols; col += 128) {
                 uint32_t k[8];
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
-                    k[u] = (c + 32 * u < cols) ? key_at(r, c + 32 * u) : KEY_SKIP;
-                    k[4 + u] = (r + 1 < rows && c + 32 * u < cols) ? key_at(r + 1, c + 32 * u) : KEY_SKIP;
+                    const bool in0 = col + 32 * u < cols, in1 = in0 && r + 1 < rows;
+                    if (shift == 24) {
+                        k[u] = in0 ? key_first(r, col + 32 * u) : KEY_SKIP;
+                        k[4 + u] = in1 ? key_first(r + 1, col + 32 * u) : KEY_SKIP;
+                    } else {
+                        k[u] = in0 ? key_at(r, col + 32 * u) : KEY_SKIP;
+                        k[4 + u] = in1 ? key_at(r + 1, col + 32 * u) : KEY_SKIP;
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++)
-                    if (k[u] != KEY_SKIP && (k[u] & prefix_mask) == prefix)
-                        atomicAdd(&hist[(k[u] >> shift) & 0xffu], 1u);
+                for (int u = 0; u < 8; u++) {
+                    if (k[u] == KEY_SKIP) continue;
+                    if ((k[u] & prefix_mask) == prefix) atomicAdd(&hist[(k[u] >> shift) & 0xffu], 1u);
+                    else if (shift == 0 && k[u] > prefix) beyond = min(beyond, k[u]);
+                }
             }
         __syncwarp();
-        uint32_t c[8], tot = 0;
-#pragma unroll
-        for (int j = 0; j < 8; j++) {
-            c[j] = hist[8 * lane + j];
-            tot += c[j];
-        }
-        const uint32_t incl = warp_scan_incl(tot, lane), excl = incl - tot;
+        ch = warp_choose_bin(hist, rank, shift == 24, lane, c);
         if (shift == 24) {
-            n_valid = __shfl_sync(FULL, incl, 31);
+            n_valid = ch.total;
             if (n_valid == 0) return td_nan();                      // warp-uniform
-            rank = (n_valid - 1) >> 1;
         }
-        const bool mine = rank >= excl && rank < incl;
-        const int src = __ffs(__ballot_sync(FULL, mine)) - 1;
-        uint32_t bin = 0, r_in = 0;
-        if (mine) {
-            uint32_t e = excl;
-#pragma unroll
-            for (int j = 0; j < 8; j++) {
-                if (rank >= e && rank < e + c[j]) {
-                    bin = 8u * (uint32_t) lane + j;
-                    r_in = rank - e;
-                }
-                e += c[j];
-            }
-        }
-        bin = __shfl_sync(FULL, bin, src);
-        rank = __shfl_sync(FULL, r_in, src);
-        prefix |= bin << shift;
+        rank = ch.r_in;
+        prefix |= ch.bin << shift;
         prefix_mask |= 0xffu << shift;
         __syncwarp();
     }
     const uint32_t lo = prefix;
-    uint32_t hi = lo;
-    if (!(n_valid & 1u)) {
-        uint32_t best = KEY_SKIP, cnt = 0;
-        for (int r = 0; r < rows; r++)
-            for (int c = lane; c < cols; c += 128) {
-                uint32_t k[4];
+    const uint32_t hi = (n_valid & 1u) ? lo : warp_upper_median(lo, ch, c, beyond, lane);
+    return warp_median_finish(lo, hi);
+}
+
+// The same for a set small enough to sit in registers (n <= 32 * PER_LANE): read once.
+template <int PER_LANE, typename KeyAt>
+__device__ float warp_median_small(const KeyAt &key_at, int n, uint32_t *hist, int lane)
+{
+    uint32_t k[PER_LANE];
 #pragma unroll
-                for (int u = 0; u < 4; u++) k[u] = (c + 32 * u < cols) ? key_at(r, c + 32 * u) : KEY_SKIP;
+    for (int u = 0; u < PER_LANE; u++) k[u] = (lane + 32 * u < n) ? key_at(lane + 32 * u) : KEY_SKIP;
+    uint32_t prefix = 0, prefix_mask = 0, rank = 0, n_valid = 0, beyond = KEY_SKIP;
+    uint32_t c[8];
+    BinChoice ch;
+#pragma unroll 1
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        for (int bin = lane; bin < 256; bin += 32) hist[bin] = 0u;
+        __syncwarp();
 #pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (k[u] != KEY_SKIP) {
-                        if (k[u] <= lo) cnt++;
-                        else best = min(best, k[u]);
-                    }
-            }
-        best = __reduce_min_sync(FULL, best);
-        cnt = __reduce_add_sync(FULL, cnt);
-        if (cnt < ((n_valid - 1) >> 1) + 2) hi = best;              // rank k + 1 is the next distinct key
+        for (int u = 0; u < PER_LANE; u++) {
+            if (k[u] == KEY_SKIP) continue;
+            if ((k[u] & prefix_mask) == prefix) atomicAdd(&hist[(k[u] >> shift) & 0xffu], 1u);
+            else if (shift == 0 && k[u] > prefix) beyond = min(beyond, k[u]);
+        }
+        __syncwarp();
+        ch = warp_choose_bin(hist, rank, shift == 24, lane, c);
+        if (shift == 24) {
+            n_valid = ch.total;
+            if (n_valid == 0) return td_nan();                      // warp-uniform
+        }
+        rank = ch.r_in;
+        prefix |= ch.bin << shift;
+        prefix_mask |= 0xffu << shift;
+        __syncwarp();
     }
-    const float a = __uint_as_float(lo), b = __uint_as_float(hi);
-    return lo == hi ? a : __fmul_rn(__fadd_rn(a, b), 0.5f);
+    const uint32_t lo = prefix;
+    const uint32_t hi = (n_valid & 1u) ? lo : warp_upper_median(lo, ch, c, beyond, lane);
+    return warp_median_finish(lo, hi);
 }
 
 // ------------------------------------------------------------------ box filter (twodflag.py:255-309)
@@ -922,22 +994,27 @@ __device__ __noinline__ void background2d(bool spectrum, int ph)
         for (int c = warp; c < a.p.n_chunks; c += TD_WARPS) {
             const int c0 = (int) a.p.chunk_ends[c], cl = (int) a.p.chunk_ends[c + 1] - c0;
             if (cl <= 0) continue;
-            for (int t = 0; t < T; t++)
-                for (int j = lane; j < cl; j += 32) {
-                    const int o = t * F + c0 + j;
-                    bg[o] = fabsf(__fsub_rn(data[o], bg[o]));
-                }
-            __syncwarp();
+            // the first pass of the select makes the residuals (and leaves them in bg)
+            auto key_first = [=](int t, int j) -> uint32_t {
+                const int o = t * F + c0 + j;
+                const float res = fabsf(__fsub_rn(data[o], bg[o]));
+                bg[o] = res;
+                return work[o] ? KEY_SKIP : __float_as_uint(res);     // residuals are >= 0
+            };
             auto key_at = [=](int t, int j) -> uint32_t {
                 const int o = t * F + c0 + j;
-                return work[o] ? KEY_SKIP : __float_as_uint(bg[o]);   // residuals are >= 0
+                return work[o] ? KEY_SKIP : __float_as_uint(bg[o]);
             };
-            const float med = warp_median(key_at, T, cl, s_whist + warp * 256, lane);
+            const float med = warp_median(key_first, key_at, T, cl, s_whist + warp * 256, lane);
             const double threshold = __dmul_rn((double) med, __dmul_rn(TD_MAD_NORMAL, a.p.background_reject));
             for (int t = 0; t < T; t++)
-                for (int j = lane; j < cl; j += 32) {
-                    const int o = t * F + c0 + j;
-                    if ((double) bg[o] > threshold) work[o] = 1;
+                for (int j = lane; j < cl; j += 128) {
+                    float res[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) res[u] = (j + 32 * u < cl) ? bg[t * F + c0 + j + 32 * u] : 0.0f;
+#pragma unroll
+                    for (int u = 0; u < 4; u++)
+                        if (j + 32 * u < cl && (double) res[u] > threshold) work[t * F + c0 + j + 32 * u] = 1;
                 }
         }
         __syncthreads();
@@ -957,8 +1034,8 @@ __device__ __noinline__ void background2d(bool spectrum, int ph)
 // hit if (cum[k + w] - cum[k]) * float32(1 / w) > lim (positive side; the negative side with
 // -scale); after the sweep every hit flags the w samples of its window.  Here: one sweep per
 // window size with the last w + 1 cumulative sums in a ring (ring[slot * L]); sample k is flagged
-// exactly if one of the windows k - w + 1 .. k fired, i.e. if any of the last w hits is set when
-// hit k has been shifted in - so the flag of sample k is final w - 1 steps after it was read, and
+// exactly if one of the windows k - w + 1 .. k fired, i.e. if the last hit is fewer than w windows
+// back when window k has been tested - so the flag of sample k is final w - 1 steps after it was read, and
 // reads of the masks (32 samples at a time) always see the state before this window size.
 // x(i), i < len: the line.  posw / negw: the line's bit masks, word j at [j * wpitch].
 template <typename LineAt>
@@ -973,19 +1050,21 @@ __device__ void sum_threshold_line(const LineAt &x_at, int len, float thr32, con
         const float lim = (float) __ddiv_rn((double) thr32, tf[wi]);
         const float nlim = -lim;
         const double scale = (double) (float) __ddiv_rn(1.0, (double) w);       // np.float32(1.0 / window)
-        const double nscale = -scale;
-        const double dlim = (double) lim;
-        const unsigned long long keep = w >= 64 ? ~0ull : ((1ull << w) - 1ull);
-        unsigned long long hits_p = 0ull, hits_n = 0ull;
+        const double dlim = (double) lim, ndlim = -dlim;
+        // "any of the last w hits": windows since the last hit (0 = this one) < w
+        int since_p = w, since_n = w;
         double cum = 0.0;
-        int head = 0;
+        double *const ring_end = ring + (int64_t) (w + 1) * L;
+        double *head = ring;                                  // the newest cumulative sum
         ring[0] = 0.0;
         uint32_t rp = 0u, rn = 0u, wp = 0u, wn = 0u;
         const int total = len + w - 1;
-        for (int i0 = 0; i0 < total; i0 += 4) {
-            float xs[4];
+        float xs[4], xn[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) xs[u] = (i0 + u < len) ? x_at(i0 + u) : 0.0f;
+        for (int u = 0; u < 4; u++) xs[u] = (u < len) ? x_at(u) : 0.0f;
+        for (int i0 = 0; i0 < total; i0 += 4) {
+#pragma unroll
+            for (int u = 0; u < 4; u++) xn[u] = (i0 + 4 + u < len) ? x_at(i0 + 4 + u) : 0.0f;   // one group ahead
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 const int i = i0 + u;
@@ -1001,22 +1080,25 @@ __device__ void sum_threshold_line(const LineAt &x_at, int len, float thr32, con
                     if ((rp & bit) && x > lim) x = lim;
                     else if ((rn & bit) && x < nlim) x = nlim;
                     cum = __dadd_rn(cum, (double) x);
-                    head = (head == w) ? 0 : head + 1;
-                    ring[head * L] = cum;
+                    head += L;
+                    if (head == ring_end) head = ring;
+                    *head = cum;
                 }
                 const int k = i + 1 - w;
                 if (k >= 0) {
-                    unsigned long long hp = 0ull, hn = 0ull;
+                    bool hp = false, hn = false;
                     if (inside) {
-                        const int oldest = (head == w) ? 0 : head + 1;
-                        const double sum = __dsub_rn(cum, ring[oldest * L]);
-                        hp = __dmul_rn(sum, scale) > dlim;
-                        hn = __dmul_rn(sum, nscale) > dlim;
+                        double *oldest = head + L;
+                        if (oldest == ring_end) oldest = ring;
+                        // sum * -scale > lim  <=>  sum * scale < -lim: negation is exact
+                        const double avg = __dmul_rn(__dsub_rn(cum, *oldest), scale);
+                        hp = avg > dlim;
+                        hn = avg < ndlim;
                     }
-                    hits_p = ((hits_p << 1) | hp) & keep;
-                    hits_n = ((hits_n << 1) | hn) & keep;
-                    wp |= (hits_p != 0ull ? 1u : 0u) << (k & 31);
-                    wn |= (hits_n != 0ull ? 1u : 0u) << (k & 31);
+                    since_p = hp ? 0 : since_p + 1;
+                    since_n = hn ? 0 : since_n + 1;
+                    wp |= (since_p < w ? 1u : 0u) << (k & 31);
+                    wn |= (since_n < w ? 1u : 0u) << (k & 31);
                     if ((k & 31) == 31 || k == len - 1) {
                         if (wp) posw[(k >> 5) * wpitch] |= wp;
                         if (wn) negw[(k >> 5) * wpitch] |= wn;
@@ -1024,6 +1106,8 @@ __device__ void sum_threshold_line(const LineAt &x_at, int len, float thr32, con
                     }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < 4; u++) xs[u] = xn[u];
         }
     }
 }
@@ -1056,7 +1140,13 @@ __device__ __noinline__ void sum_threshold_freq(bool spectrum, int ph)
         auto key_at = [=](int, int j) -> uint32_t {
             return frow[j] ? KEY_SKIP : (__float_as_uint(row[j]) & 0x7fffffffu);
         };
-        const float med = warp_median(key_at, 1, cl, s_whist + warp * 256, lane);
+        float med;
+        if (cl <= 512) {
+            auto key1 = [=](int j) -> uint32_t { return key_at(0, j); };
+            med = warp_median_small<16>(key1, cl, s_whist + warp * 256, lane);
+        } else {
+            med = warp_median(key_at, key_at, 1, cl, s_whist + warp * 256, lane);
+        }
         if (lane == 0) b.thr[i] = scaled_threshold(med, a.p.outlier_nsigma);
     }
     __syncthreads();
