@@ -555,6 +555,15 @@ struct BoxStage {
         A::store(rp, in);
         return en;
     }
+    // The same when the stage both adds and pops (add_limit > it >= pop_start): no conditions.
+    __device__ __forceinline__ typename A::Val step_steady(typename A::Val in, float *rp)
+    {
+        const typename A::Sum sa = A::add(s, in);
+        e = A::round(sa);
+        s = A::sub(sa, A::load(rp));
+        A::store(rp, in);
+        return e;
+    }
 };
 
 // float32(2 r + 1) ** K as numba evaluates it: binary exponentiation in float32 (K = 4: the
@@ -785,12 +794,16 @@ __device__ __noinline__ void box_freq_pass(const float *__restrict__ data, const
             }
             asm volatile("cp.async.commit_group;" ::: "memory");
         };
+        // threads without a line run the same instructions on a word of their own (no branch in
+        // the loops: a divergence check around every shuffle costs as much as the stage itself)
+        float *const my_ring = active ? ring : reinterpret_cast<float *>(s_whist) + tid;
+        const int my_stride = active ? rstride : 0;
         if (active)
             for (int s = 0; s < r2; s++) ring[s * rstride] = 0.0f;
         BoxStage<BoxF64> st;
         st.init(p, F, r2);
         const bool head = active && p == 0, tail = active && p == 3;
-        float *rp = ring;
+        float *rp = my_ring;
         int slot = 0, tb = 0;
         request(tiles, 0);
         for (int step0 = 0; step0 < total; step0 += 32, tb ^= 1) {
@@ -804,19 +817,31 @@ __device__ __noinline__ void box_freq_pass(const float *__restrict__ data, const
             __syncwarp();
             float *cell = tile + ll * 33;
             const int kmax = min(32, total - step0);
+            if (step0 >= 2 * r2 + 3 && step0 + 32 <= F) {
+                // the bulk of the line: every stage adds and pops in all 32 iterations of the tile
+#pragma unroll 4
+                for (int k = 0; k < 32; k++) {
+                    const float from_prev = td_shfl_up1(st.e);
+                    const float en = st.step_steady(head ? cell[k] : from_prev, rp);
+                    if (tail) cell[k] = en;
+                    slot++;
+                    rp += my_stride;
+                    if (slot == r2) {
+                        slot = 0;
+                        rp = my_ring;
+                    }
+                }
+            } else
             for (int k = 0; k < kmax; k++) {
                 const float from_prev = td_shfl_up1(st.e);
                 const float x = head ? cell[k] : from_prev;
-                if (active) {
-                    const int it = step0 + k;
-                    const float en = st.step(it, x, rp);
-                    if (tail) cell[k] = en;                            // unnormalised; only positions >= 0 are used
-                }
+                const float en = st.step(step0 + k, x, rp);
+                if (tail) cell[k] = en;                                // unnormalised; only positions >= 0 are used
                 slot++;
-                rp += rstride;
+                rp += my_stride;
                 if (slot == r2) {
                     slot = 0;
-                    rp = ring;
+                    rp = my_ring;
                 }
             }
             __syncwarp();
