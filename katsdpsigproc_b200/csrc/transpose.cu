@@ -6,8 +6,10 @@
 // tile order is the plain one; what matters is that both the loads and the
 // stores of a warp cover whole 32-byte sectors.
 //
-//   * 4/8/16-byte elements: 32x32-element tile, 32x8 threads, 4 rows per thread;
-//     a warp reads 128/256/512 contiguous bytes and writes the same.
+//   * 4-byte elements of 16-byte aligned arrays: 64x64 tile moved with 128-bit loads and
+//     stores (transpose_words128_kernel).
+//   * otherwise 4/8-byte elements: 32x32-element tile, 32x8 threads, 4 rows per thread;
+//     a warp reads 128/256 contiguous bytes and writes the same.
 //   * 1/2-byte elements (flags): 128x32... handled by the BYTES variant below: a
 //     64x64-element tile moved as 32-bit words (16 lanes per 64-byte row), and
 //     re-packed from shared memory so that the stores are 32-bit words too.
@@ -135,6 +137,56 @@ transpose_bytes128_kernel(uint8_t *__restrict__ dst, const uint8_t *__restrict__
         __stcs(reinterpret_cast<uint4 *>(out + k * dst_stride), make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]));
 }
 
+// 4-byte elements of 16-byte aligned arrays: 64 x 64 tile, 128-bit loads (a warp reads two rows
+// of 256 contiguous bytes), the tile stored as 16-byte chunks with an XOR swizzle (chunk ch of
+// row r at ch ^ (r / 4 & 7): conflict-free both ways, no padding), every thread takes a 4 x 4
+// block as four 128-bit shared loads - the transposition of the block is only a renaming of
+// registers - and writes four 128-bit rows, 16 lanes filling 256 contiguous bytes.  Ragged
+// tiles at the right and bottom edges go element by element through the same tile.
+__global__ void __launch_bounds__(256)
+transpose_words128_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, int64_t rows,
+                          int64_t cols, int64_t dst_stride, int64_t src_stride)
+{
+    __shared__ __align__(16) uint32_t tile[64 * 64];
+    const int64_t c0 = (int64_t) blockIdx.x * 64;
+    const int64_t r0 = (int64_t) blockIdx.y * 64;
+    const int t = threadIdx.x;
+    if (r0 + 64 <= rows && c0 + 64 <= cols) {
+        uint4 v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int q = t + 256 * k, r = q >> 4, ch = q & 15;
+            v[k] = __ldcs(reinterpret_cast<const uint4 *>(src + (r0 + r) * src_stride + c0 + 4 * ch));
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int q = t + 256 * k, r = q >> 4, ch = q & 15;
+            *reinterpret_cast<uint4 *>(&tile[r * 64 + 4 * (ch ^ ((r >> 2) & 7))]) = v[k];
+        }
+        __syncthreads();
+        const int rg = t & 15, cg = t >> 4;               // source rows 4 rg .., columns 4 cg ..
+        uint4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            w[i] = *reinterpret_cast<const uint4 *>(&tile[(4 * rg + i) * 64 + 4 * (cg ^ (rg & 7))]);
+        uint32_t *out = dst + (c0 + 4 * cg) * dst_stride + r0 + 4 * rg;
+        __stcs(reinterpret_cast<uint4 *>(out), make_uint4(w[0].x, w[1].x, w[2].x, w[3].x));
+        __stcs(reinterpret_cast<uint4 *>(out + dst_stride), make_uint4(w[0].y, w[1].y, w[2].y, w[3].y));
+        __stcs(reinterpret_cast<uint4 *>(out + 2 * dst_stride), make_uint4(w[0].z, w[1].z, w[2].z, w[3].z));
+        __stcs(reinterpret_cast<uint4 *>(out + 3 * dst_stride), make_uint4(w[0].w, w[1].w, w[2].w, w[3].w));
+    } else {
+        for (int i = t; i < 64 * 64; i += 256) {
+            const int r = i >> 6, c = i & 63;
+            if (r0 + r < rows && c0 + c < cols) tile[r * 64 + ((c + r) & 63)] = src[(r0 + r) * src_stride + c0 + c];
+        }
+        __syncthreads();
+        for (int i = t; i < 64 * 64; i += 256) {
+            const int c = i >> 6, r = i & 63;
+            if (r0 + r < rows && c0 + c < cols) dst[(c0 + c) * dst_stride + r0 + r] = tile[r * 64 + ((c + r) & 63)];
+        }
+    }
+}
+
 // Plain transposition written with the fusable tools of include/ksp_transpose_base.cuh (the
 // reference's transpose.mako:44-73 is the same metakernel with these two bodies); used for the
 // element sizes off the flagger's path (2 and 16 bytes).
@@ -230,7 +282,18 @@ extern "C" int ksp_transpose(void *stream, void *dst, const void *src, int64_t r
         return rest(0, 0, rows, cols);
     }
     case 2: return launch_base<uint16_t>(s, dst, src, rows, cols, dst_stride, src_stride);
-    case 4: return launch_tile<uint32_t>(s, dst, src, rows, cols, dst_stride, src_stride);
+    case 4: {
+        const bool a16 = ((uintptr_t) dst % 16 == 0) && ((uintptr_t) src % 16 == 0) &&
+                         (dst_stride % 4 == 0) && (src_stride % 4 == 0);
+        if (!a16 || rows < 64 || cols < 64)
+            return launch_tile<uint32_t>(s, dst, src, rows, cols, dst_stride, src_stride);
+        dim3 grid((unsigned) ksp_divup(cols, 64), (unsigned) ksp_divup(rows, 64));
+        if (grid.y > 65535) return KSP_ETOOLARGE;
+        transpose_words128_kernel<<<grid, 256, 0, s>>>((uint32_t *) dst, (const uint32_t *) src, rows,
+                                                       cols, dst_stride, src_stride);
+        KSP_CHECK_LAUNCH();
+        return 0;
+    }
     case 8: return launch_tile<uint2>(s, dst, src, rows, cols, dst_stride, src_stride);
     case 16: return launch_base<uint4>(s, dst, src, rows, cols, dst_stride, src_stride);
     default: return KSP_EINVAL;

@@ -61,6 +61,17 @@ def test_transpose_bytes_128bit_tiles(shape, pads):
     np.testing.assert_array_equal(a.T, cu.transpose(a, *pads))
 
 
+@pytest.mark.parametrize("shape,pads", [((64, 64), (0, 0)), ((256, 384), (0, 0)), ((300, 500), (0, 0)),
+                                        ((128, 192), (4, 8)), ((391, 132), (0, 1)), ((200, 333), (3, 0)),
+                                        ((1024, 640), (0, 16)), ((640, 1), (0, 0)), ((65, 4160), (0, 0))])
+def test_transpose_words_128bit_tiles(shape, pads):
+    """float32 arrays with 16-byte aligned rows take the 64 x 64-tile kernel with 128-bit loads and
+    stores (ragged edge tiles element by element); misaligned ones take the 32 x 32 one."""
+    rs = np.random.RandomState(4)
+    a = rs.standard_normal(shape).astype(np.float32)
+    np.testing.assert_array_equal(a.T, cu.transpose(a, *pads))
+
+
 def test_transpose_rejects_bad_element_size():
     from ctypes import c_void_p
 
@@ -477,6 +488,25 @@ def test_masked_sum(abs_mode, cols, use_amplitudes):
     data = (np.abs(src).astype(np.float64) if use_amplitudes else src.astype(np.complex128))
     ref = np.sum(data * mask[:, None], axis=0)
     assert np.all(np.abs(ref - out) <= 1e-6 * scale)
+
+
+@pytest.mark.parametrize("rows,cols,pad", [(1, 1, 0), (3, 33, 1), (255, 31, 1), (256, 32, 0),
+                                           (700, 1, 1), (5000, 97, 1), (5000, 97, 0), (2049, 640, 0),
+                                           (300, 9000, 0)])
+@pytest.mark.parametrize("use_amplitudes", [False, True])
+def test_masked_sum_geometry(abs_mode, rows, cols, pad, use_amplitudes):
+    """Row splits of 1 to 8 blocks per strip of columns (a thread block cluster), one or two
+    columns per lane (odd last column, odd strides), fewer rows than row groups, no rows."""
+    rs = np.random.RandomState(rows * 131 + cols)
+    src = complex_normal(rs, (rows, cols))
+    mask = rs.uniform(0, 2, rows).astype(np.float32)
+    out = cu.masked_sum(src, mask, use_amplitudes, abs_mode, pad=pad)
+    data = (contract.amplitude(src.ravel(), abs_mode).reshape(src.shape).astype(np.float64)
+            if use_amplitudes else src.astype(np.complex128))
+    ref = np.sum(data * mask.astype(np.float64)[:, None], axis=0)
+    scale = np.sum(np.abs(src) * mask[:, None], axis=0)
+    assert out.shape == (cols,)
+    assert np.all(np.abs(ref - out) <= 1e-7 * scale + 1e-30)
 
 
 # ------------------------------------------------------------------ amplitude rule (R1)
