@@ -567,7 +567,7 @@ def chunked_form(template, queue, flagger, C: int, B: int, steps: int, timed, pe
              "threshold": "threshold_sum_kernel (two passes)", "expand_flags": "expand_flags_kernel"}
     n_vis = C * B
     out = {
-        "what": "four launches per chunk of 2368 baselines; deviations go through device memory",
+        "what": "background filter of the whole dump in one launch, then noise, two threshold passes and flag expansion per chunk of 2368 baselines on 4 lanes; deviations go through device memory",
         "ms_per_step_4_lanes": ms_lanes,
         "ms_per_step_1_lane_sum_of_stages": sum(v[0] for v in stages.values()) / steps,
         "stage_ms_per_step": {k: v[0] / steps for k, v in stages.items()},
