@@ -200,6 +200,23 @@ __device__ __forceinline__ void stream_key_checked(float x, float lo_f, float hi
     }
 }
 
+// Developer aid (tools/micro/madnz_phases.cu): cycles of thread 0 of every block between the ticks
+#ifdef MS_PHASE_CLOCK
+__device__ unsigned long long ms_phase[8];
+#define MS_TICK(k)                                                                              \
+    do {                                                                                        \
+        if (threadIdx.x == 0) {                                                                 \
+            const long long now__ = clock64();                                                  \
+            atomicAdd(&ms_phase[k], (unsigned long long) (now__ - tick__));                     \
+            tick__ = now__;                                                                     \
+        }                                                                                       \
+    } while (0)
+#define MS_TICK_START() long long tick__ = clock64()
+#else
+#define MS_TICK(k) do { } while (0)
+#define MS_TICK_START() do { } while (0)
+#endif
+
 // Shared memory of one row: lists, hist, coarse, misc in this order.
 constexpr int MS_SMEM_WORDS = MS_SLOTS * MS_THREADS + MS_BINS + MS_BINS / 32 + 160;
 
@@ -235,6 +252,7 @@ __device__ __forceinline__ void madnz_stream_row(const float *__restrict__ row, 
         if (tid == 0) *noise_out = __int_as_float(0x7fc00000);
         return;
     }
+    MS_TICK_START();
     // the sample histogram of step 1 borrows the (still unused) list memory
     uint32_t *s_fine = lists, *s_coarse = lists + MS_BINS;
     for (int i = tid; i < MS_BINS; i += MS_THREADS) {
@@ -297,6 +315,7 @@ __device__ __forceinline__ void madnz_stream_row(const float *__restrict__ row, 
         }
         const uint32_t q_lo = wide ? MS_QLO_WIDE : MS_QLO, q_hi = wide ? MS_QHI_WIDE : MS_QHI;
         __syncthreads();
+        MS_TICK(0);
         const uint32_t c0 = s_coarse[2 * lane];
         const uint32_t c01 = c0 + s_coarse[2 * lane + 1];
         const uint32_t c_incl = warp_scan_incl(c01, lane), c_excl = c_incl - c01;
@@ -316,6 +335,7 @@ __device__ __forceinline__ void madnz_stream_row(const float *__restrict__ row, 
             hi = max(hi, lo);
         }
         __syncthreads();                              // the lists may now overwrite the sample histogram
+        MS_TICK(1);
     }
     const uint32_t width = hi - lo + 1u;
 
@@ -381,6 +401,7 @@ __device__ __forceinline__ void madnz_stream_row(const float *__restrict__ row, 
             atomicAdd(&misc[12], kept_w);
             if (over_w) misc[2] = 1u;
         }
+        MS_TICK(2);
     }
 
     // ---- 3. select inside the lists.  Histogram of the kept keys at two levels (2048 bins and
@@ -394,6 +415,7 @@ __device__ __forceinline__ void madnz_stream_row(const float *__restrict__ row, 
         atomicAdd(&coarse[b >> 5], 1u);
     }
     __syncthreads();
+    MS_TICK(3);
     const uint32_t n_valid = misc[0];
     if (n_valid == 0) {                                       // block-uniform
         if (tid == 0) *noise_out = __int_as_float(0x7fc00000);
@@ -429,6 +451,7 @@ __device__ __forceinline__ void madnz_stream_row(const float *__restrict__ row, 
         beyond = __reduce_min_sync(0xffffffffu, beyond);
         if (lane == 0 && beyond < 0x80000000u) atomicMin(&misc[10], beyond);
         __syncthreads();
+        MS_TICK(4);
         if (crowded) {
             fallback = true;                                  // heavy ties: block-uniform
         } else {
@@ -445,6 +468,7 @@ __device__ __forceinline__ void madnz_stream_row(const float *__restrict__ row, 
                 const uint32_t v2 = !even ? v1 : (h.r_in + 1u < h.count ? nxt : bin_first + span + misc[10]);
                 if (lane == 0) *noise_out = mad_finish(v1, v2);
             }
+            MS_TICK(5);
             return;
         }
     }

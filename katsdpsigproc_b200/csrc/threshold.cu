@@ -270,14 +270,95 @@ threshold_simple_kernel(const float *__restrict__ dev, const float *__restrict__
 
 // ---------------------------------------------------------------- packed flags -> bytes (threshold_tile.cuh)
 
-__global__ void __launch_bounds__(256)
+// Tile: 256 baselines x 8 words (256 channels) by 128 threads.  A thread owns 16 consecutive
+// baselines of one word (32 channels): 16 words in, 32 rows of 16 flag bytes out, each row ONE
+// 128-bit streaming store - the 16 lanes that share a word fill 256 contiguous bytes of a flags row.
+// Bits become bytes through a 256-entry table in shared memory (8 flags per 64-bit load; flags
+// are sparse, so almost every lookup is the broadcast of entry 0) and the 4 x 4 byte blocks are
+// transposed with byte permutes: about one instruction per flag byte (the 32-bit stores of
+// expand_flags_tile, which the dataflow kernel keeps, cost 4.2).
+constexpr int EX_THREADS = 128;
+constexpr int EX_BL = 256;               // baselines per tile
+constexpr int EX_WORDS = 8;              // words per tile
+constexpr int EX_PITCH = 20;             // words per group of 16 baselines: conflict-free 128-bit reads
+
+__device__ __forceinline__ void stg_stream_u4(uint8_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d)
+{
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(a), "r"(b), "r"(c),
+                 "r"(d), "l"(l2_evict_first())
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(EX_THREADS)
 expand_flags_kernel(const uint32_t *__restrict__ bits_t, uint8_t *__restrict__ flags,
                     int64_t channels, int64_t baselines, int64_t wstride, int64_t fstride,
                     int flag_value)
 {
-    __shared__ __align__(16) uint32_t tile[8][132];
-    expand_flags_tile<false>(bits_t, flags, channels, baselines, wstride, fstride, flag_value,
-                             (int64_t) blockIdx.x * 128, (int64_t) blockIdx.y * 8, 0, tile);
+    __shared__ __align__(16) uint32_t tile[EX_WORDS][EX_BL / 16][EX_PITCH];
+    __shared__ __align__(8) uint2 lut[256];
+    const int t = threadIdx.x;
+    const int64_t b0 = (int64_t) blockIdx.x * EX_BL, w0 = (int64_t) blockIdx.y * EX_WORDS;
+    const int64_t n_words = (channels + 31) >> 5;
+    const uint32_t fv = (uint32_t) flag_value & 0xffu;
+    for (int v = t; v < 256; v += EX_THREADS)           // byte of 8 flag bits -> 8 flag bytes
+        lut[v] = make_uint2((((uint32_t) v & 0xfu) * 0x00204081u & 0x01010101u) * fv,
+                            (((uint32_t) v >> 4) * 0x00204081u & 0x01010101u) * fv);
+#pragma unroll
+    for (int k = 0; k < EX_BL * EX_WORDS / EX_THREADS; k++) {
+        const int i = t + EX_THREADS * k, w = i & (EX_WORDS - 1), b = i / EX_WORDS;
+        uint32_t v = 0;
+        if (b0 + b < baselines && w0 + w < n_words) v = __ldg(bits_t + (b0 + b) * wstride + w0 + w);
+        tile[w][b >> 4][b & 15] = v;
+    }
+    __syncthreads();
+    const int bg = t & 15, w = t >> 4;
+    if (w0 + w >= n_words) return;
+    uint32_t wv[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(&tile[w][bg][4 * k]);
+        wv[4 * k] = q.x; wv[4 * k + 1] = q.y; wv[4 * k + 2] = q.z; wv[4 * k + 3] = q.w;
+    }
+    const int64_t c_base = (w0 + w) * 32;
+    const int64_t b = b0 + 16 * bg;
+    if (b >= baselines) return;
+    const bool vec = (b + 16 <= baselines) && (c_base + 32 <= channels) && ((fstride & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(flags) & 15) == 0);
+    if (vec) {
+        uint8_t *out = flags + c_base * fstride + b;
+#pragma unroll
+        for (int h = 0; h < 4; h++) {                   // channels 8 h .. 8 h + 7
+            uint2 e[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) e[i] = lut[(wv[i] >> (8 * h)) & 0xffu];
+#pragma unroll
+            for (int half = 0; half < 2; half++) {      // channels 8 h + 4 half .. + 3
+                uint32_t o[4][4];                       // o[k][j]: channel k, baselines 4 j .. 4 j + 3
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t r0 = half ? e[4 * j].y : e[4 * j].x, r1 = half ? e[4 * j + 1].y : e[4 * j + 1].x;
+                    const uint32_t r2 = half ? e[4 * j + 2].y : e[4 * j + 2].x, r3 = half ? e[4 * j + 3].y : e[4 * j + 3].x;
+                    // r_i: byte k = channel k of baseline 4 j + i; o[k][j]: byte i = baseline 4 j + i
+                    const uint32_t a01 = __byte_perm(r0, r1, 0x5140), b01 = __byte_perm(r0, r1, 0x7362);
+                    const uint32_t a23 = __byte_perm(r2, r3, 0x5140), b23 = __byte_perm(r2, r3, 0x7362);
+                    o[0][j] = __byte_perm(a01, a23, 0x5410);
+                    o[1][j] = __byte_perm(a01, a23, 0x7632);
+                    o[2][j] = __byte_perm(b01, b23, 0x5410);
+                    o[3][j] = __byte_perm(b01, b23, 0x7632);
+                }
+                uint8_t *row = out + (int64_t) (8 * h + 4 * half) * fstride;
+#pragma unroll
+                for (int k = 0; k < 4; k++)             // write-once output: first to leave the L2
+                    stg_stream_u4(row + k * fstride, o[k][0], o[k][1], o[k][2], o[k][3]);
+            }
+        }
+        return;
+    }
+    // ragged edges, unaligned output: flag by flag
+    for (int bit = 0; bit < 32 && c_base + bit < channels; bit++)
+#pragma unroll 4
+        for (int i = 0; i < 16; i++)
+            if (b + i < baselines) flags[(c_base + bit) * fstride + b + i] = (uint8_t) (((wv[i] >> bit) & 1u) * fv);
 }
 
 // ---------------------------------------------------------------- more than 7 window sizes
@@ -605,9 +686,9 @@ int ksp_expand_flags(cudaStream_t s, const uint32_t *bits_t, uint8_t *flags, int
                      int64_t baselines, int64_t words_stride, int64_t flags_stride, int flag_value)
 {
     if (channels == 0 || baselines == 0) return 0;
-    dim3 grid((unsigned) ksp_divup(baselines, 128), (unsigned) ksp_divup(ksp_divup(channels, 32), 8));
+    dim3 grid((unsigned) ksp_divup(baselines, EX_BL), (unsigned) ksp_divup(ksp_divup(channels, 32), EX_WORDS));
     if (grid.y > 65535) return KSP_ETOOLARGE;
-    expand_flags_kernel<<<grid, 256, 0, s>>>(bits_t, flags, channels, baselines, words_stride,
+    expand_flags_kernel<<<grid, EX_THREADS, 0, s>>>(bits_t, flags, channels, baselines, words_stride,
                                              flags_stride, flag_value);
     KSP_CHECK_LAUNCH();
     return 0;
