@@ -196,18 +196,23 @@ extern "C" int ksp_flagger(void *stream, const ksp_flagger_params *p, const void
     // With several lanes, chunk i runs on internal stream i % lanes with its own scratch; the
     // internal streams fork from and join back into the caller's stream through events, so
     // the call keeps plain stream semantics.
-    // When every chunk has a lane of its own (the usual case), the background filter of ALL chunks
-    // is ONE launch on the caller's stream - the lanes' deviations are contiguous in the scratch -
-    // and only the later stages run chunk by chunk on the lanes: the background kernel gains
-    // nothing from sharing the SMs with the other stages (measured: stream priorities that
-    // interleave them cost 18 %), and a launch over the whole dump has one ramp and one tail
-    // instead of one per chunk (0.61 against 0.72 ms when the stages are timed one after the other).
-    // KSP_BG_WHOLE=0 restores a launch per chunk.
-    static const bool env_bg_whole = [] {
+    // When every chunk has a lane of its own, the background filter of ALL chunks can be ONE launch
+    // on the caller's stream - the lanes' deviations are contiguous in the scratch - with only the
+    // later stages chunk by chunk on the lanes: one ramp and one tail instead of one per chunk
+    // (0.61 against 0.72 ms at 8320 baselines with the stages timed one after the other).  Measured
+    // with 4 lanes (profiles/r02g_bg_whole.txt): the same at 8320 baselines (1.107 ms, 13 launches
+    // instead of 16), 1.5 % faster at 12960, but 1 - 6 % SLOWER for the shards of a dump split over
+    // 2 - 8 GPUs (6496 ... 1632 baselines), where the first chunk's noise estimate had better
+    // start under the second chunk's background tiles.  So: dumps of at least 3 chunk units with
+    // the library's own chunking; a caller who fixes chunk_baselines gets it whenever the chunks
+    // fit the lanes.  KSP_BG_WHOLE=0 / 1: never / wherever the chunks fit the lanes.
+    static const int env_bg_whole = [] {
         const char *e = getenv("KSP_BG_WHOLE");
-        return !(e && atoi(e) == 0);
+        return e ? atoi(e) : -1;
     }();
-    const bool bg_whole = env_bg_whole && ksp_divup(p->baselines, l.chunk) <= l.lanes;
+    const bool fits = ksp_divup(p->baselines, l.chunk) <= l.lanes;
+    const bool large = p->chunk_baselines > 0 || p->baselines >= 3 * 16 * (int64_t) ksp_sm_count();
+    const bool bg_whole = fits && (env_bg_whole < 0 ? large : env_bg_whole != 0);
     if (bg_whole) {
         ksp_profile_begin(KSP_STAGE_BACKGROUND, user);
         int rc = ksp_background_median_filter_t(user, vis, (float *) scratch, input_flags, p->channels,

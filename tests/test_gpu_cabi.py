@@ -408,6 +408,28 @@ def test_flagger_fused_medium(abs_mode):
     np.testing.assert_array_equal(flags, out_flags)
 
 
+@pytest.mark.parametrize("flag_kind", ["none", "channel", "full"])
+def test_flagger_fused_more_chunks_than_lanes(abs_mode, flag_kind):
+    """With more chunks than lanes every chunk launches its own background filter (with up to 4
+    chunks one launch covers them all); baselines not a multiple of 16 or 32, padded and
+    unpadded flag rows (128-bit and byte-wise flag expansion)."""
+    rs = np.random.RandomState(11)
+    channels, baselines = 2048, 203
+    vis = complex_normal(rs, (channels, baselines))
+    vis[rs.random_sample(vis.shape) < 1 / 64] += 40.0
+    vis[700:730, ::3] += 2.5
+    fl = None
+    if flag_kind == "channel":
+        fl = (rs.random_sample(channels) < 0.05).astype(np.uint8)
+    elif flag_kind == "full":
+        fl = (rs.random_sample(vis.shape) < 0.05).astype(np.uint8)
+    flags, dev, noise = contract.flagger(vis, fl, n_windows=7, abs_mode=abs_mode)
+    for chunk, pad in ((32, 0), (32, 5), (64, 13), (0, 0)):
+        out_flags, out_noise = cu.flagger(vis, fl, n_windows=7, abs_mode=abs_mode, chunk_baselines=chunk, pad=pad)
+        assert_same_f32(noise, out_noise)
+        np.testing.assert_array_equal(flags, out_flags)
+
+
 # ------------------------------------------------------------------ helpers
 @pytest.mark.parametrize("shape,column_range", [((4096, 1), None), ((4096, 4029), None),
                                                 ((64, 300), (8, 280)), ((27, 301), (0, 301)),

@@ -71,7 +71,7 @@ def main():
                           "bg13_kernel": pick("bg13_kernel<0, 0, 1", "(260, 128, 1)"),
                           "madnz_stream_kernel": pick("madnz_stream_kernel", "(2368, 1, 1)"),
                           "threshold_sum_kernel": pick("threshold_sum_kernel<1, 128, 1>", "(1332, 1, 1)"),
-                          "expand_flags_kernel": pick("expand_flags_kernel", "(19, 128, 1)")},
+                          "expand_flags_kernel": pick("expand_flags_kernel", "(10, 128, 1)")},
               "what": "dram__bytes_read.sum + dram__bytes_write.sum per launch; bg13_kernel covers the whole "
                       "8320-baseline dump, the other launches are those of a 2368-baseline chunk"}
     with open(os.path.join(ROOT, "profiles", "roofline_traffic.json"), "w") as f:
