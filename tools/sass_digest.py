@@ -88,7 +88,7 @@ def main():
                 lines.append("")
                 return
 
-    excerpt(r"bg13_kernel<0, 0, 1, 256>", "FMNMX3", 8, 150, "phase 2 of the background tile: shared selection network (FMNMX3 / FMNMX) and the deviations")
+    excerpt(r"bg13_kernel<0, 0, true, 256>", "FMNMX3", 8, 150, "phase 2 of the background tile: shared selection network (FMNMX3 / FMNMX) and the deviations")
     excerpt(r"madnz_stream_kernel", "LDG.E.128", 2, 90, "the pass over the row: three compares, two predicated counters, predicated append per key")
     excerpt(r"threshold_sum_kernel<true, 128, 1>", "UTMALDG", 12, 12, "TMA tile load of a span and its mbarrier")
     excerpt(r"maskedsum_kernel<false, 2>", "UCGABAR", 20, 30, "cluster barrier and the reads of the other blocks' partial strips")
