@@ -132,6 +132,25 @@ def test_noise_est(context, command_queue, transposed):
     np.testing.assert_allclose(hn.noise_est_mad(deviations), out, rtol=2e-7)
 
 
+@pytest.mark.parametrize("shape", [(2048, 37), (4100, 70), (2047, 33)])
+def test_noise_est_channel_major_long_rows(context, command_queue, shape):
+    """From NoiseEstMADDevice.TRANSPOSE_FROM channels on, the channel-major operation transposes
+    into its scratch_t slot and runs the baseline-major kernel; shorter rows (2047) use the
+    channel-major kernel.  Zeros and NaN are skipped either way; an all-zero baseline gives NaN."""
+    rs = np.random.RandomState(5)
+    deviations = rs.standard_normal(shape).astype(np.float32)
+    deviations[rs.random_sample(shape) < 0.05] = 0.0
+    deviations[rs.random_sample(shape) < 0.01] = np.nan
+    deviations[:, 3] = 0.0
+    template = rfi.NoiseEstMADDeviceTemplate(context)
+    fn = template.instantiate(command_queue, *shape)
+    assert ("scratch_t" in fn.slots) == (shape[0] >= fn.TRANSPOSE_FROM)
+    out = rfi.NoiseEstHostFromDevice(template, command_queue)(deviations)
+    expect = contract.noise_mad(deviations)[0]
+    assert same_bits(expect, out)
+    assert np.isnan(out[3])
+
+
 def threshold_case():
     rs = np.random.RandomState(1)
     deviations = rs.standard_normal((117, 273)).astype(np.float32) * 10.0

@@ -98,6 +98,11 @@ def main():
         print("madnz_t fallback rows", fb.value, "of", B, flush=True)
         rec("madnz", timeit(lambda: _capi.call(
             "ksp_madnz", S, p(dev_cm), p(noise), C, B, B), args.reps, flush), 4)
+        # what NoiseEstMADDevice runs for long rows: transposition into its scratch, then the row kernel
+        def madnz_via_transpose():
+            _capi.call("ksp_transpose", S, p(dev_t), p(dev_cm), C, B, CT, B, 4)
+            _capi.call("ksp_madnz_t", S, p(dev_t), p(noise), C, B, CT)
+        rec("madnz_via_transpose", timeit(madnz_via_transpose, args.reps, flush), 4)
         rec("threshold_sum7", timeit(lambda: _capi.call(
             "ksp_threshold_sum", S, p(dev_t), p(noise), p(flags_t), C, B, CT, CT, 7, c_double(11.0), sc7, 1),
             args.reps, flush), 5)
