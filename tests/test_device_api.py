@@ -75,6 +75,23 @@ def test_noise_templates(context, queue):
     assert slot_table(op) == {"noise": ((273,), np.float32), "deviations": ((117, 273), np.float32)}
 
 
+def test_noise_channel_major_long_rows_slot(context, queue):
+    """From TRANSPOSE_FROM channels on, the channel-major operation owns a transposed scratch
+    (it runs the baseline-major kernel behind one transposition); inside an unfused flagger the
+    slot is exported under the child's name and allocated with the rest."""
+    T = rfi.NoiseEstMADDeviceTemplate(context)
+    short = T.instantiate(queue, rfi.NoiseEstMADDevice.TRANSPOSE_FROM - 1, 40)
+    assert "scratch_t" not in short.slots
+    op = T.instantiate(queue, 4096, 40)
+    assert slot_table(op) == {"noise": ((40,), np.float32), "deviations": ((4096, 40), np.float32),
+                              "scratch_t": ((40, 4096), np.float32)}
+    template = make_flagger(context, False, False, fused=False)
+    fn = template.instantiate(queue, 4096, 40, threshold_args={"n_sigma": 11.0})
+    assert set(fn.slots) == {"vis", "deviations", "noise", "flags", "noise_est:scratch_t"}
+    fn.ensure_all_bound()
+    assert fn.noise_est.buffer("scratch_t").shape == (40, 4096)
+
+
 def test_threshold_templates(context, queue):
     with pytest.raises(ValueError):
         rfi.ThresholdSumDeviceTemplate(context, n_windows=12)
