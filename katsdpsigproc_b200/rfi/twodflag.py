@@ -173,22 +173,45 @@ class SumThresholdFlagger:
             else:
                 np.not_equal(flags[rows], 0, out=h_flags[rows])
 
+        # Time slices: staged by the pool's threads (numpy copies release the GIL) and uploaded one
+        # by one as they become ready, so the upload of the first slices runs under the staging of
+        # the later ones; small inputs take the plain path.
         n_time = data.shape[0]
-        workers = min(_STAGING_THREADS, n_time) if data.nbytes >= (64 << 20) else 1
-        if workers > 1:                                            # numpy copies release the GIL
-            bounds = np.linspace(0, n_time, workers + 1).astype(int)
-            list(_staging_pool().map(stage, [slice(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:])]))
+        stream = ctypes.c_void_p(queue.stream)
+        row_items = int(np.prod(data.shape[1:]))
+
+        def upload(rows: slice) -> None:
+            for dev, host in ((buf["d_data"], buf["h_data"]), (buf["d_flags"], buf["h_flags"])):
+                step = row_items * host.dtype.itemsize
+                _capi.call("ksp_memcpy_async", ctypes.c_void_p(dev.buffer.ptr + rows.start * step),
+                           ctypes.c_void_p(host.ctypes.data + rows.start * step),
+                           c_size_t((rows.stop - rows.start) * step), _capi.H2D, stream)
+
+        large = data.nbytes >= (64 << 20) and n_time > 1
+        slices = [slice(None)]
+        if large:
+            bounds = np.linspace(0, n_time, min(n_time, 2 * _STAGING_THREADS) + 1).astype(int)
+            slices = [slice(int(a), int(b)) for a, b in zip(bounds[:-1], bounds[1:])]
+            for rows, done in zip(slices, [_staging_pool().submit(stage, rows) for rows in slices]):
+                done.result()
+                upload(rows)
         else:
             stage(slice(None))
-        buf["d_data"].set_async(queue, buf["h_data"])
-        buf["d_flags"].set_async(queue, buf["h_flags"])
-        _capi.call("ksp_twodflag", ctypes.c_void_p(queue.stream), byref(p),
+            buf["d_data"].set_async(queue, buf["h_data"])
+            buf["d_flags"].set_async(queue, buf["h_flags"])
+        _capi.call("ksp_twodflag", stream, byref(p),
                    ctypes.c_void_p(buf["d_data"].buffer.ptr), ctypes.c_void_p(buf["d_flags"].buffer.ptr),
                    ctypes.c_void_p(buf["d_out"].buffer.ptr), ctypes.c_void_p(buf["d_scratch"].buffer.ptr),
                    c_size_t(per_baseline * chunk_size), ctypes.c_int64(chunk_size))
         buf["d_out"].get_async(queue, buf["h_out"])
         queue.finish()
-        return np.array(buf["h_out"].view(np.bool_))               # the kernel writes 0 / 1: a copy the caller owns
+        # the kernel writes 0 / 1; the caller gets a copy it owns
+        h_out = buf["h_out"].view(np.bool_)
+        if not large:
+            return np.array(h_out)
+        out = np.empty(data.shape, np.bool_)
+        list(_staging_pool().map(lambda rows: np.copyto(out[rows], h_out[rows]), slices))
+        return out
 
     def _buffers_for(self, context: Any, shape: Sequence[int], dtype: Any, scratch_bytes: int) -> dict:
         """Device arrays and pinned staging arrays for one input shape, kept from call to call
